@@ -1,0 +1,193 @@
+/*
+ * h264_recon_b200.h — C ABI of the B200 H.264 picture-reconstruction engine.
+ *
+ * This is the drop-in boundary for the hot path of jfu222/h264_video_decoder_demo:
+ * everything the reference does per macroblock AFTER entropy decoding and
+ * motion/mode derivation, i.e.
+ *
+ *   - residual:  dequant + 4x4 / 8x8 / DC inverse transforms
+ *                (reference: H264PictureBase.cpp:3401-3929, 3989-4402, 4993-5088,
+ *                 H264InterPrediction.cpp:22-407)
+ *   - inter:     luma 6-tap / chroma bilinear MC, default/explicit/implicit
+ *                weighting (H264InterPrediction.cpp:412-667, 2051-2829)
+ *   - intra:     4x4 / 8x8 / 16x16 / chroma prediction (H264PictureBase.cpp:1062-2499)
+ *   - deblock:   bS derivation + edge filters (H264PictureDeblockingFilterProcess.cpp:76-1522)
+ *   - DPB pixel storage (H264PictureBase.cpp:128-233; zero-at-reuse :45-69)
+ *
+ * The reference has no FFI for this path (it is reached by member calls from
+ * CH264SliceData::slice_data, H264SliceData.cpp:222-227, 333-338, 400-487 and
+ * from end_decode_the_picture_and_get_a_new_empty_picture, H264PictureBase.cpp:707).
+ * The host side (serial entropy decode + derivations) replaces those calls by
+ * "append this macroblock to the picture's structure-of-arrays" and hands the
+ * finished picture to h264b2_submit().  Plain pointers and sizes only.
+ *
+ * Conventions follow the reference: every function returns int, 0 = ok,
+ * negative = failure; no exceptions; one context per GPU; calls on one
+ * context must come from one thread at a time.
+ */
+#ifndef H264_RECON_B200_H
+#define H264_RECON_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H264B2_ABI_VERSION 1
+
+/* ---- macroblock classes (derived from CH264MacroBlock::m_mb_pred_mode /
+ *      m_name_of_mb_type, H264MacroBlock.h:210-211) ---- */
+enum {
+    H264B2_MB_NA    = 0,  /* never decoded (MB_TYPE_NA): pixels stay 0, deblock stops here (Q2) */
+    H264B2_MB_I4x4  = 1,  /* Intra_4x4   */
+    H264B2_MB_I8x8  = 2,  /* Intra_8x8   */
+    H264B2_MB_I16x16= 3,  /* Intra_16x16 */
+    H264B2_MB_IPCM  = 4,  /* I_PCM (pred mode Intra_NA: NOT "intra" for bS, Q11) */
+    H264B2_MB_INTER = 5   /* every P_* / B_* type incl. skip and direct */
+};
+
+/* H264B2MbInfo.flags */
+#define H264B2_MBF_FIELD        0x01  /* mb_field_decoding_flag (MBAFF field macroblock) */
+#define H264B2_MBF_T8x8         0x02  /* transform_size_8x8_flag */
+#define H264B2_MBF_SPSI         0x04  /* slice_type of the MB's slice is SP or SI (bS rules) */
+#define H264B2_MBF_CIP_UNAVAIL  0x08  /* IS_INTER_Prediction_Mode(mode) && constrained_intra_pred_flag:
+                                         samples of this MB are "not available" to intra neighbours
+                                         (H264PictureBase.cpp:1129, 1492, 1905, 2158; Q12) */
+
+/* coef_mask bits: which coefficient blocks of the MB are present in the
+ * coefficient stream (blocks that are absent are all-zero).  Blocks are stored
+ * back to back, in this bit order, starting at coef_offset (units: int16). */
+#define H264B2_CM_LUMA(b)   (1u << (b))      /* b=0..15: luma 4x4 block b (luma4x4BlkIdx), 16 int16 in
+                                                list order (LumaLevel4x4[b][k]; for Intra16x16 k=0 is
+                                                unused and k=1..15 = Intra16x16ACLevel[b][k-1]).
+                                                With T8x8: b=0..3 = LumaLevel8x8[b][0..63], 64 int16. */
+#define H264B2_CM_LUMA_DC   (1u << 16)       /* Intra16x16DCLevel[0..15], 16 int16 */
+#define H264B2_CM_CHROMA_DC (1u << 17)       /* ChromaDCLevel[0][0..3] then [1][0..3], 8 int16 */
+#define H264B2_CM_CB(b)     (1u << (18 + (b))) /* b=0..3: 16 int16, k=0 unused, k=1..15 = ChromaACLevel[0][b][k-1] */
+#define H264B2_CM_CR(b)     (1u << (22 + (b))) /* b=0..3: same for Cr */
+#define H264B2_CM_PCM       (1u << 26)       /* I_PCM: 384 samples stored as 384 int16 (256 Y, 64 Cb, 64 Cr) */
+
+typedef struct H264B2MbInfo {      /* 16 bytes, one per macroblock address */
+    uint8_t  mb_class;             /* H264B2_MB_* */
+    uint8_t  flags;                /* H264B2_MBF_* */
+    uint8_t  pred16_chroma;        /* bits0-1 Intra16x16PredMode, bits2-3 intra_chroma_pred_mode */
+    int8_t   qpy;                  /* QPY (== QP'Y at 8 bit); the value deblocking reads (DB:898) */
+    uint16_t slice_number;         /* CH264MacroBlock::slice_number: neighbour availability (PB:2890) */
+    uint16_t nnz_mask;             /* bit b: transform block covering luma4x4BlkIdx b has non-zero
+                                      levels, exactly as DB:1124-1143 tests it (Q18) */
+    int8_t   filter_offset_a;      /* FilterOffsetA of the MB's slice (DB:884) */
+    int8_t   filter_offset_b;
+    uint8_t  deblock_idc;          /* disable_deblocking_filter_idc of the MB's slice */
+    uint8_t  reserved;
+    uint32_t coef_mask;            /* H264B2_CM_* */
+} H264B2MbInfo;
+
+typedef struct H264B2MbMotion {    /* 152 bytes, one per macroblock address (inter MBs only are read) */
+    int16_t mv[2][16][2];          /* [list][4x4 block in RASTER order y*4+x][x,y], quarter-pel
+                                      (flattening of m_MvL0/L1[mbPart][subMbPart], IP:593-597) */
+    int8_t  ref_surf[2][4];        /* [list][8x8 quadrant]: -1 = list unused (predFlag 0), else
+                                      (dpb_surface << 2) | view, view 0 frame / 1 top field / 2 bottom
+                                      field: the result of Reference_picture_selection_process (IP:2117) */
+    int8_t  ref_ident[2][4];       /* picture identity for bS "same reference picture" tests, computed
+                                      the way DB:1175-1178 does (raw refIdx into the picture's last-built
+                                      list, Q6); -1 = NULL */
+    uint16_t wt_idx[4];            /* [8x8 quadrant] index into the picture's weight table */
+} H264B2MbMotion;
+
+typedef struct H264B2Weight {      /* 32 bytes; entry 0 of every table must be the default entry */
+    int16_t mode;                  /* 0 = default weighted prediction (IP:2617), 1 = explicit/implicit formula (IP:2699) */
+    int16_t logwd[3];              /* [Y,Cb,Cr] */
+    int16_t w0[3], w1[3];          /* weight applied to the list-0 / list-1 prediction */
+    int16_t o0[3], o1[3];          /* offsets; for single-list prediction from list 1 the device uses
+                                      w1/o1, so the host puts whatever the reference would use there (Q8) */
+} H264B2Weight;
+
+typedef struct H264B2PicParams {
+    int32_t  width_mbs;            /* PicWidthInMbs */
+    int32_t  height_mbs;           /* frame height in MBs (68 for 1088) */
+    int32_t  mbaff_frame_flag;     /* MbaffFrameFlag; field pictures (PAFF) are rejected (Q16) */
+    int32_t  chroma_qp_offset[2];  /* chroma_qp_index_offset, second_chroma_qp_index_offset */
+    int32_t  dst_surface;          /* DPB surface this picture is reconstructed into */
+    int32_t  clear_surface;        /* 1: zero the surface first (PB:53-69); required when some MB is NA */
+    int32_t  has_inter;            /* 0: no inter MB in the picture (motion may be NULL) */
+    int32_t  deblock_enable;       /* 0: leave the picture un-deblocked (last picture of a stream, Q1) */
+    int32_t  deblock_stop_mb;      /* deblock MB addresses [0, stop) only (first NA MB, Q2) */
+    int32_t  n_weights;            /* entries in weights[] (>= 1) */
+    uint32_t n_coefs;              /* int16 elements in coefs[] */
+    int32_t  custom_scaling;       /* 0: Flat_4x4_16 / Flat_8x8_16; 1: level_scale4/8 given */
+    int32_t  reserved;
+    /* host (or device, see h264b2_submit_device) arrays */
+    const H264B2MbInfo   *mb_info;     /* [width_mbs*height_mbs] */
+    const uint64_t       *intra_modes; /* [n_mbs] 16 x 4 bit: Intra4x4PredMode[b] (b=luma4x4BlkIdx) or
+                                          Intra8x8PredMode[b] in nibbles 0..3 */
+    const uint32_t       *coef_offset; /* [n_mbs] int16 index of the MB's first coefficient block */
+    const H264B2MbMotion *motion;      /* [n_mbs] */
+    const H264B2Weight   *weights;     /* [n_weights] */
+    const int16_t        *coefs;       /* [n_coefs] */
+    const int16_t        *level_scale4;/* optional [2 intra/inter][2 frame/field scan][6][16] (list order k) */
+    const int16_t        *level_scale8;/* optional [2][2][6][64] */
+} H264B2PicParams;
+
+typedef struct H264B2Context H264B2Context;
+
+/* Create a per-GPU context: n_streams independent streams, each with
+ * surfaces_per_stream DPB surfaces (the reference keeps 16 pictures,
+ * H264PicturesGOP.h:27) of width_mbs x height_mbs macroblocks, I420,
+ * Y|Cb|Cr contiguous in one allocation like PB:167-179. */
+int h264b2_create(H264B2Context **ctx, int device, int n_streams, int surfaces_per_stream,
+                  int width_mbs, int height_mbs);
+int h264b2_destroy(H264B2Context *ctx);
+
+/* Reconstruct one picture per listed stream (pictures of one stream are serial;
+ * pictures of different streams run concurrently in one launch sequence).
+ * Host arrays are copied to the device asynchronously from pinned staging;
+ * the call returns after enqueueing.  stream_ids[i] in [0, n_streams). */
+int h264b2_submit(H264B2Context *ctx, int n_pics, const int32_t *stream_ids,
+                  const H264B2PicParams *pics);
+
+/* Same, but every array pointer in pics[] is already a device pointer
+ * (pre-parsed buffers resident in HBM: the replay path the bench's `value` times). */
+int h264b2_submit_device(H264B2Context *ctx, int n_pics, const int32_t *stream_ids,
+                         const H264B2PicParams *pics);
+
+/* Copy a reconstructed surface to host I420 (width_mbs*16 x height_mbs*16, 3/2 bytes per pixel).
+ * Synchronises with all prior work on the context. */
+int h264b2_read_picture(H264B2Context *ctx, int stream_id, int surface, uint8_t *host_i420);
+
+/* Write a surface from host I420 (used by tests to seed reference pictures). */
+int h264b2_write_picture(H264B2Context *ctx, int stream_id, int surface, const uint8_t *host_i420);
+
+/* 64-bit positional checksum of a surface computed on the GPU (the only data
+ * that has to leave the GPU in the multi-stream/multi-GPU configuration). */
+int h264b2_checksum_picture(H264B2Context *ctx, int stream_id, int surface, uint64_t *checksum);
+
+/* Device pointer of a surface (Y plane; Cb = Y + W*H, Cr = Cb + W*H/4). */
+int h264b2_surface_ptr(H264B2Context *ctx, int stream_id, int surface, void **dev_ptr);
+
+/* Device-memory helpers so that non-CUDA hosts can make buffers resident. */
+int h264b2_dev_alloc(H264B2Context *ctx, size_t bytes, void **dev_ptr);
+int h264b2_dev_free(H264B2Context *ctx, void *dev_ptr);
+int h264b2_dev_upload(H264B2Context *ctx, void *dev_dst, const void *host_src, size_t bytes);
+
+/* Block until all enqueued work is done. */
+int h264b2_sync(H264B2Context *ctx);
+
+/* Event timing on the context's launch stream (CUDA events; for bench.py). */
+int h264b2_timer_start(H264B2Context *ctx);
+int h264b2_timer_stop(H264B2Context *ctx, float *elapsed_ms);
+/* Per-kernel-class accumulated time of the last timed region (ms): [clear, residual+inter, intra, bs, deblock]. */
+int h264b2_kernel_times(H264B2Context *ctx, float *ms5, int64_t *launches);
+
+/* ABI version / last error string (static storage). */
+int h264b2_abi_version(void);
+const char *h264b2_last_error(void);
+
+/* checksum used throughout: sum over little-endian u32 words w_i of (w_i + 1) * ((2*i+1) * 0x9E3779B97F4A7C15) mod 2^64 */
+uint64_t h264b2_checksum_host(const uint8_t *data, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H264_RECON_B200_H */

@@ -1,0 +1,52 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle_recon.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.run(["make", "-C", _HERE, "port"], check=True, capture_output=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle_recon.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.oracle_reconstruct_picture.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]
+        _LIB.oracle_reconstruct_picture.restype = C.c_int
+        _LIB.oracle_checksum.argtypes = [C.c_void_p, C.c_size_t]
+        _LIB.oracle_checksum.restype = C.c_uint64
+    return _LIB
+
+
+STAGE_RECON, STAGE_DEBLOCK = 1, 2
+
+
+class OracleDPB:
+    """n_surfaces host I420 surfaces + the oracle's reconstruct call."""
+
+    def __init__(self, width_mbs, height_mbs, n_surfaces=17):
+        self.frame_bytes = width_mbs * height_mbs * 384
+        self.surfaces = [np.zeros(self.frame_bytes, dtype=np.uint8) for _ in range(n_surfaces)]
+        self._ptrs = (C.c_void_p * n_surfaces)(*[s.ctypes.data for s in self.surfaces])
+        self.n = n_surfaces
+
+    def reconstruct(self, params, stages=STAGE_RECON | STAGE_DEBLOCK):
+        r = lib().oracle_reconstruct_picture(C.addressof(params), self._ptrs, self.n, stages)
+        if r != 0:
+            raise RuntimeError(f"oracle_reconstruct_picture failed: {r}")
+
+    def checksum(self, slot):
+        s = self.surfaces[slot]
+        return int(lib().oracle_checksum(s.ctypes.data, s.size))
