@@ -1,0 +1,458 @@
+// engine.cu — per-GPU context, launch sequencing and the C ABI of include/h264_recon_b200.h.
+//
+// One context = one GPU.  A submit reconstructs one picture for each listed stream (pictures of one
+// stream are serial in decoding order; different streams are independent and share every launch):
+//
+//   [memset of surfaces that must start from zero (PB:53-69)]
+//   k_inter    inter prediction + inter residual        (fully parallel, one CTA per macroblock)
+//   k_intra    intra prediction + intra residual        (MB wavefront, one warp per MB row)
+//   k_bs       boundary strengths                        (fully parallel)
+//   k_deblock  in-loop filter, in place                  (MB wavefront, one warp per MB row)
+//
+// The decoded picture buffer (n_streams x surfaces_per_stream I420 surfaces, Y|Cb|Cr contiguous like
+// PB:167-179) lives in HBM for the life of the context.  There is no CPU fallback anywhere.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <new>
+
+#include "h264_recon_b200.h"
+#include "common.cuh"
+#include "residual.cuh"
+#include "inter.cuh"
+#include "intra.cuh"
+#include "deblock.cuh"
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(-10, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ------------------------------------------------------------------ checksum kernel
+__global__ void k_checksum(const uint8_t *const *surf, size_t nwords, unsigned long long *out) {
+    const uint32_t *w = (const uint32_t *)surf[blockIdx.y];
+    const unsigned long long K = 0x9E3779B97F4A7C15ULL;
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x)
+        acc += ((unsigned long long)w[i] + 1ULL) * ((2ULL * i + 1ULL) * K);
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&out[blockIdx.y], acc);
+}
+
+// ------------------------------------------------------------------ context
+enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 8192, KCLASSES = 5 };
+
+struct H264B2Context {
+    int device, n_streams, spp, wmb, hmb, nmb;
+    size_t frame_bytes;
+    uint8_t *surfaces;
+    uint32_t *bs;
+    int *progress;            // [n_streams][2][hmb] then DESC_RING*2 tickets
+    size_t progress_ints;
+    int16_t *ls_flat;         // ls4 [2][2][6][16] then ls8 [2][2][6][64]
+    cudaStream_t st, st_h2d, st_d2h;
+    // descriptor ring
+    PicDev *h_desc, *d_desc;
+    cudaEvent_t desc_ev[DESC_RING];
+    int desc_next;
+    // host-submit staging: device arena slots
+    uint8_t *arena[NSLOT]; size_t arena_cap[NSLOT];
+    cudaEvent_t h2d_done[NSLOT], compute_done[NSLOT];
+    int slot_next;
+    // read-back staging
+    uint8_t *out_stage[2]; size_t out_cap[2]; cudaEvent_t out_ready[2], out_done[2]; int out_next;
+    uint8_t **d_ptrs; unsigned long long *d_sums; unsigned long long *h_sums; uint8_t **h_ptrs;
+    // timing
+    cudaEvent_t t0, t1;
+    int timing;
+    cudaEvent_t *ev; int ev_used; int ev_class[EV_POOL / 2];
+    float class_ms[KCLASSES]; long long class_launches[KCLASSES];
+};
+
+static const uint8_t h_zz4[16] = {0,1,4,8, 5,2,3,6, 9,12,13,10, 7,11,14,15};
+static const uint8_t h_fs4[16] = {0,4,1,8, 12,5,9,13, 2,6,10,14, 3,7,11,15};
+static const uint8_t h_fs8[64] = {
+     0, 8,16, 1, 9,24,32,17,  2,25,40,48,56,33,10, 3,
+    18,41,49,57,26,11, 4,19, 34,42,50,58,27,12, 5,20,
+    35,43,51,59,28,13, 6,21, 36,44,52,60,29,14,22,37,
+    45,53,61,30, 7,15,38,46, 54,62,23,31,39,47,55,63 };
+static const int h_na4[6][3] = {{10,16,13},{11,18,14},{13,20,16},{14,23,18},{16,25,20},{18,29,23}};
+static const int h_na8[6][6] = {{20,18,32,19,25,24},{22,19,35,21,28,26},{26,23,42,24,33,31},{28,25,45,26,35,33},{32,28,51,30,40,38},{36,32,58,34,46,43}};
+static int na4(int m, int pos) { int i = pos >> 2, j = pos & 3; return (!(i & 1) && !(j & 1)) ? h_na4[m][0] : ((i & 1) && (j & 1)) ? h_na4[m][1] : h_na4[m][2]; }
+static int na8(int m, int pos) {
+    int i = pos >> 3, j = pos & 7;
+    if (i % 4 == 0 && j % 4 == 0) return h_na8[m][0];
+    if (i % 2 == 1 && j % 2 == 1) return h_na8[m][1];
+    if (i % 4 == 2 && j % 4 == 2) return h_na8[m][2];
+    if ((i % 4 == 0 && j % 2 == 1) || (i % 2 == 1 && j % 4 == 0)) return h_na8[m][3];
+    if ((i % 4 == 0 && j % 4 == 2) || (i % 4 == 2 && j % 4 == 0)) return h_na8[m][4];
+    return h_na8[m][5];
+}
+
+static int init_tables(H264B2Context *c) {
+    uint8_t zz8[64];
+    { int i = 0, j = 0;
+      for (int k = 0; k < 64; k++) {
+          zz8[k] = (uint8_t)(i * 8 + j);
+          if ((i + j) % 2 == 0) { if (j == 7) i++; else if (i == 0) j++; else { i--; j++; } }
+          else { if (i == 7) j++; else if (j == 0) i++; else { i++; j--; } }
+      } }
+    uint8_t is4[2][16], is8[2][64];
+    for (int k = 0; k < 16; k++) { is4[0][h_zz4[k]] = (uint8_t)k; is4[1][h_fs4[k]] = (uint8_t)k; }
+    for (int k = 0; k < 64; k++) { is8[0][zz8[k]] = (uint8_t)k; is8[1][h_fs8[k]] = (uint8_t)k; }
+    CK(cudaMemcpyToSymbol(c_iscan4, is4, sizeof is4));
+    CK(cudaMemcpyToSymbol(c_iscan8, is8, sizeof is8));
+    // Flat_4x4_16 / Flat_8x8_16 LevelScale in list order (PB:4852-4989 with weightScale = 16)
+    std::vector<int16_t> ls(2 * 2 * 6 * 16 + 2 * 2 * 6 * 64);
+    size_t o = 0;
+    for (int inter = 0; inter < 2; inter++) for (int f = 0; f < 2; f++) for (int m = 0; m < 6; m++)
+        for (int k = 0; k < 16; k++) ls[o++] = (int16_t)(16 * na4(m, f ? h_fs4[k] : h_zz4[k]));
+    for (int inter = 0; inter < 2; inter++) for (int f = 0; f < 2; f++) for (int m = 0; m < 6; m++)
+        for (int k = 0; k < 64; k++) ls[o++] = (int16_t)(16 * na8(m, f ? h_fs8[k] : zz8[k]));
+    CK(cudaMalloc(&c->ls_flat, ls.size() * 2));
+    CK(cudaMemcpy(c->ls_flat, ls.data(), ls.size() * 2, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int h264b2_abi_version(void) { return H264B2_ABI_VERSION; }
+extern "C" const char *h264b2_last_error(void) { return g_err; }
+
+extern "C" uint64_t h264b2_checksum_host(const uint8_t *data, size_t bytes) {
+    const uint64_t K = 0x9E3779B97F4A7C15ULL;
+    uint64_t acc = 0; const size_t nw = bytes / 4;
+    for (size_t i = 0; i < nw; i++) { uint32_t w; memcpy(&w, data + 4 * i, 4); acc += ((uint64_t)w + 1) * ((2 * (uint64_t)i + 1) * K); }
+    return acc;
+}
+
+extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int surfaces_per_stream, int width_mbs, int height_mbs) {
+    if (!out || n_streams < 1 || surfaces_per_stream < 1 || surfaces_per_stream > 32 || width_mbs < 1 || height_mbs < 1)
+        return fail(-1, "h264b2_create: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(-11, "h264b2_create: no CUDA device (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(-1, "h264b2_create: device %d out of range", device);
+    CK(cudaSetDevice(device));
+    H264B2Context *c = new (std::nothrow) H264B2Context();
+    if (!c) return fail(-12, "out of memory");
+    memset(c, 0, sizeof *c);
+    c->device = device; c->n_streams = n_streams; c->spp = surfaces_per_stream; c->wmb = width_mbs; c->hmb = height_mbs;
+    c->nmb = width_mbs * height_mbs; c->frame_bytes = (size_t)c->nmb * 384;
+    const size_t total = (size_t)n_streams * surfaces_per_stream * c->frame_bytes;
+    // tail padding: a bottom-field view clamps x to 2W-1 and may read one row past the last plane (Q4)
+    CK(cudaMalloc(&c->surfaces, total + (size_t)width_mbs * 64));
+    CK(cudaMemset(c->surfaces, 0, total + (size_t)width_mbs * 64));
+    CK(cudaMalloc(&c->bs, (size_t)n_streams * c->nmb * 65 * 4));
+    c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 2;
+    CK(cudaMalloc(&c->progress, c->progress_ints * 4));
+    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+    CK(cudaMallocHost(&c->h_desc, sizeof(PicDev) * n_streams * DESC_RING));
+    CK(cudaMalloc(&c->d_desc, sizeof(PicDev) * n_streams * DESC_RING));
+    for (int i = 0; i < DESC_RING; i++) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < NSLOT; i++) { CK(cudaEventCreateWithFlags(&c->h2d_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming)); }
+    for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->out_ready[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming)); }
+    CK(cudaMalloc(&c->d_ptrs, sizeof(uint8_t *) * n_streams));
+    CK(cudaMalloc(&c->d_sums, 8 * n_streams));
+    CK(cudaMallocHost(&c->h_sums, 8 * n_streams));
+    CK(cudaMallocHost(&c->h_ptrs, sizeof(uint8_t *) * n_streams));
+    CK(cudaEventCreate(&c->t0)); CK(cudaEventCreate(&c->t1));
+    c->ev = (cudaEvent_t *)calloc(EV_POOL, sizeof(cudaEvent_t));
+    if (init_tables(c)) return -10;
+    *out = c;
+    return 0;
+}
+
+extern "C" int h264b2_destroy(H264B2Context *c) {
+    if (!c) return fail(-1, "null context");
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc);
+    for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->compute_done[i]); }
+    for (int i = 0; i < 2; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
+    for (int i = 0; i < DESC_RING; i++) cudaEventDestroy(c->desc_ev[i]);
+    cudaFree(c->d_ptrs); cudaFree(c->d_sums); cudaFreeHost(c->h_sums); cudaFreeHost(c->h_ptrs);
+    for (int i = 0; i < EV_POOL; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    free(c->ev);
+    cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
+    cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_d2h);
+    delete c;
+    return 0;
+}
+
+// ------------------------------------------------------------------ timing helpers
+static void class_begin(H264B2Context *c, int cls) {
+    if (!c->timing || c->ev_used + 2 > EV_POOL) return;
+    for (int i = 0; i < 2; i++) if (!c->ev[c->ev_used + i]) cudaEventCreate(&c->ev[c->ev_used + i]);
+    c->ev_class[c->ev_used / 2] = cls;
+    cudaEventRecord(c->ev[c->ev_used], c->st);
+}
+static void class_end(H264B2Context *c, int cls) {
+    c->class_launches[cls]++;
+    if (!c->timing || c->ev_used + 2 > EV_POOL) return;
+    cudaEventRecord(c->ev[c->ev_used + 1], c->st);
+    c->ev_used += 2;
+}
+
+static int validate(const H264B2Context *c, int n_pics, const int32_t *sids, const H264B2PicParams *pics) {
+    if (!c || n_pics < 1 || n_pics > c->n_streams || !sids || !pics) return fail(-1, "submit: bad argument");
+    std::vector<char> seen(c->n_streams, 0);
+    for (int i = 0; i < n_pics; i++) {
+        const H264B2PicParams &p = pics[i];
+        if (sids[i] < 0 || sids[i] >= c->n_streams) return fail(-2, "submit: stream id %d out of range", sids[i]);
+        if (seen[sids[i]]) return fail(-2, "submit: stream %d listed twice (pictures of one stream are serial)", sids[i]);
+        seen[sids[i]] = 1;
+        if (p.width_mbs != c->wmb || p.height_mbs != c->hmb) return fail(-3, "submit: picture is %dx%d MBs, context is %dx%d", p.width_mbs, p.height_mbs, c->wmb, c->hmb);
+        if (p.dst_surface < 0 || p.dst_surface >= c->spp) return fail(-3, "submit: dst_surface %d out of range", p.dst_surface);
+        if (p.mbaff_frame_flag && (c->hmb & 1)) return fail(-3, "submit: MBAFF picture with odd height in MBs");
+        if (!p.mb_info || !p.intra_modes || !p.coef_offset || !p.weights || p.n_weights < 1) return fail(-3, "submit: missing array");
+        if (p.has_inter && !p.motion) return fail(-3, "submit: has_inter without motion");
+        if (p.n_coefs && !p.coefs) return fail(-3, "submit: n_coefs without coefs");
+        if (p.custom_scaling && (!p.level_scale4 || !p.level_scale8)) return fail(-3, "submit: custom_scaling without tables");
+    }
+    return 0;
+}
+
+// enqueue the kernels of one batch; every array pointer in pics[] is a device pointer
+static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264B2PicParams *pics) {
+    const int ring = c->desc_next; c->desc_next = (c->desc_next + 1) % DESC_RING;
+    CK(cudaEventSynchronize(c->desc_ev[ring]));
+    PicDev *hd = c->h_desc + (size_t)ring * c->n_streams, *dd = c->d_desc + (size_t)ring * c->n_streams;
+    int any_inter = 0, any_deblock = 0;
+    for (int i = 0; i < n; i++) {
+        const H264B2PicParams &p = pics[i];
+        PicDev &d = hd[i];
+        d.info = p.mb_info; d.modes = p.intra_modes; d.coef_off = p.coef_offset; d.motion = p.has_inter ? p.motion : nullptr;
+        d.weights = p.weights; d.coefs = p.coefs;
+        d.ls4 = p.custom_scaling ? p.level_scale4 : c->ls_flat;
+        d.ls8 = p.custom_scaling ? p.level_scale8 : c->ls_flat + 2 * 2 * 6 * 16;
+        d.stream_base = c->surfaces + (size_t)sids[i] * c->spp * c->frame_bytes;
+        d.dst = (uint8_t *)d.stream_base + (size_t)p.dst_surface * c->frame_bytes;
+        d.bs = c->bs + (size_t)sids[i] * c->nmb * 65;
+        d.progress = c->progress + (size_t)sids[i] * 2 * c->hmb;
+        d.frame_bytes = c->frame_bytes;
+        d.wmb = c->wmb; d.hmb = c->hmb; d.mbaff = p.mbaff_frame_flag; d.cqp0 = p.chroma_qp_offset[0]; d.cqp1 = p.chroma_qp_offset[1];
+        d.deblock_enable = p.deblock_enable; d.deblock_stop = p.deblock_stop_mb < c->nmb ? p.deblock_stop_mb : c->nmb;
+        d.n_weights = p.n_weights; d.reserved = 0;
+        any_inter |= p.has_inter; any_deblock |= p.deblock_enable;
+    }
+    CK(cudaMemcpyAsync(dd, hd, sizeof(PicDev) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaEventRecord(c->desc_ev[ring], c->st));
+    int *tickets = c->progress + (c->progress_ints - DESC_RING * 2) + ring * 2;
+    class_begin(c, 0);
+    CK(cudaMemsetAsync(c->progress, 0, c->progress_ints * 4, c->st));
+    for (int i = 0; i < n; i++) if (pics[i].clear_surface) CK(cudaMemsetAsync(hd[i].dst, 0, c->frame_bytes, c->st));
+    class_end(c, 0);
+    if (any_inter) {
+        class_begin(c, 1);
+        k_inter<<<dim3(c->nmb, n), 256, 0, c->st>>>(dd);
+        class_end(c, 1);
+    }
+    const int rows_total = n * c->hmb;
+    class_begin(c, 2);
+    k_intra<<<(rows_total + 3) / 4, 128, 0, c->st>>>(dd, n, c->hmb, tickets);
+    class_end(c, 2);
+    if (any_deblock) {
+        class_begin(c, 3);
+        k_bs<<<dim3((c->nmb + 7) / 8, n), 256, 0, c->st>>>(dd);
+        class_end(c, 3);
+        class_begin(c, 4);
+        k_deblock<<<(rows_total + 3) / 4, 128, 0, c->st>>>(dd, n, c->hmb, tickets + 1);
+        class_end(c, 4);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int h264b2_submit_device(H264B2Context *c, int n_pics, const int32_t *sids, const H264B2PicParams *pics) {
+    int r = validate(c, n_pics, sids, pics);
+    if (r) return r;
+    CK(cudaSetDevice(c->device));
+    return launch_batch(c, n_pics, sids, pics);
+}
+
+// ---- host-array submit: one DMA per contiguous span, straight from the caller's memory (pinned memory
+// from h264b2_host_alloc makes the copies asynchronous; pageable memory works but is staged by the driver).
+struct Span { const uint8_t *p; size_t n; const void **slot; };
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, const H264B2PicParams *pics) {
+    int r = validate(c, n_pics, sids, pics);
+    if (r) return r;
+    CK(cudaSetDevice(c->device));
+    const int slot = c->slot_next; c->slot_next = (c->slot_next + 1) % NSLOT;
+    std::vector<H264B2PicParams> dev(pics, pics + n_pics);
+    // plan
+    size_t need = 0;
+    std::vector<Span> spans; spans.reserve((size_t)n_pics * 8);
+    for (int i = 0; i < n_pics; i++) {
+        H264B2PicParams &p = dev[i];
+        const size_t nmb = (size_t)c->nmb;
+        Span s[8] = {
+            { (const uint8_t *)p.mb_info, nmb * sizeof(H264B2MbInfo), (const void **)&p.mb_info },
+            { (const uint8_t *)p.intra_modes, nmb * 8, (const void **)&p.intra_modes },
+            { (const uint8_t *)p.coef_offset, nmb * 4, (const void **)&p.coef_offset },
+            { (const uint8_t *)(p.has_inter ? p.motion : nullptr), p.has_inter ? nmb * sizeof(H264B2MbMotion) : 0, (const void **)&p.motion },
+            { (const uint8_t *)p.weights, (size_t)p.n_weights * sizeof(H264B2Weight), (const void **)&p.weights },
+            { (const uint8_t *)p.coefs, (size_t)p.n_coefs * 2, (const void **)&p.coefs },
+            { (const uint8_t *)(p.custom_scaling ? p.level_scale4 : nullptr), p.custom_scaling ? (size_t)2 * 2 * 6 * 16 * 2 : 0, (const void **)&p.level_scale4 },
+            { (const uint8_t *)(p.custom_scaling ? p.level_scale8 : nullptr), p.custom_scaling ? (size_t)2 * 2 * 6 * 64 * 2 : 0, (const void **)&p.level_scale8 },
+        };
+        for (int k = 0; k < 8; k++) { if (s[k].n) { spans.push_back(s[k]); need += al256(s[k].n) + 256; } else *s[k].slot = nullptr; }
+    }
+    if (c->arena_cap[slot] < need) {
+        CK(cudaEventSynchronize(c->compute_done[slot]));
+        if (c->arena[slot]) CK(cudaFree(c->arena[slot]));
+        c->arena_cap[slot] = need + need / 4;
+        CK(cudaMalloc(&c->arena[slot], c->arena_cap[slot]));
+    }
+    CK(cudaStreamWaitEvent(c->st_h2d, c->compute_done[slot], 0));
+    // copy: merge spans that are adjacent in host memory (same relative alignment kept)
+    size_t off = 0;
+    size_t i = 0;
+    while (i < spans.size()) {
+        size_t j = i;
+        const uint8_t *lo = spans[i].p; const uint8_t *hi = lo + spans[i].n;
+        while (j + 1 < spans.size() && spans[j + 1].p >= hi && (size_t)(spans[j + 1].p - hi) <= 64) { j++; hi = spans[j].p + spans[j].n; }
+        // keep the host address's offset within 256 so that every array keeps its natural alignment
+        off = al256(off) + ((size_t)(uintptr_t)lo & 255);
+        CK(cudaMemcpyAsync(c->arena[slot] + off, lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, c->st_h2d));
+        for (size_t k = i; k <= j; k++) *spans[k].slot = c->arena[slot] + off + (spans[k].p - lo);
+        off += (size_t)(hi - lo);
+        i = j + 1;
+    }
+    CK(cudaEventRecord(c->h2d_done[slot], c->st_h2d));
+    CK(cudaStreamWaitEvent(c->st, c->h2d_done[slot], 0));
+    r = launch_batch(c, n_pics, sids, dev.data());
+    if (r) return r;
+    CK(cudaEventRecord(c->compute_done[slot], c->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------ surfaces
+static int surf_ptr(H264B2Context *c, int sid, int surface, uint8_t **p) {
+    if (!c || sid < 0 || sid >= c->n_streams || surface < 0 || surface >= c->spp) return fail(-2, "stream/surface out of range");
+    *p = c->surfaces + ((size_t)sid * c->spp + surface) * c->frame_bytes;
+    return 0;
+}
+extern "C" int h264b2_surface_ptr(H264B2Context *c, int sid, int surface, void **dev_ptr) {
+    uint8_t *p; int r = surf_ptr(c, sid, surface, &p); if (r) return r; *dev_ptr = p; return 0;
+}
+extern "C" int h264b2_sync(H264B2Context *c) {
+    if (!c) return fail(-1, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st_h2d)); CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_d2h));
+    return 0;
+}
+extern "C" int h264b2_read_picture(H264B2Context *c, int sid, int surface, uint8_t *host) {
+    uint8_t *p; int r = surf_ptr(c, sid, surface, &p); if (r) return r;
+    if (!host) return fail(-1, "null host pointer");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(host, p, c->frame_bytes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+extern "C" int h264b2_write_picture(H264B2Context *c, int sid, int surface, const uint8_t *host) {
+    uint8_t *p; int r = surf_ptr(c, sid, surface, &p); if (r) return r;
+    if (!host) return fail(-1, "null host pointer");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(p, host, c->frame_bytes, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+// Asynchronous read-back of n surfaces (n <= n_streams) into host memory (pinned for true overlap): the
+// surfaces are snapshotted device-to-device on the launch stream, then drained to the host on a separate
+// stream so the next submit does not wait for PCIe.  Complete after h264b2_sync().
+extern "C" int h264b2_read_pictures_async(H264B2Context *c, int n, const int32_t *sids, const int32_t *surfaces, uint8_t *const *host) {
+    if (!c || n < 1 || n > c->n_streams || !sids || !surfaces || !host) return fail(-1, "read_pictures_async: bad argument");
+    CK(cudaSetDevice(c->device));
+    const int s = c->out_next; c->out_next ^= 1;
+    const size_t need = (size_t)n * c->frame_bytes;
+    if (c->out_cap[s] < need) {
+        CK(cudaEventSynchronize(c->out_done[s]));
+        if (c->out_stage[s]) CK(cudaFree(c->out_stage[s]));
+        c->out_cap[s] = (size_t)c->n_streams * c->frame_bytes;
+        CK(cudaMalloc(&c->out_stage[s], c->out_cap[s]));
+    }
+    CK(cudaStreamWaitEvent(c->st, c->out_done[s], 0));
+    for (int i = 0; i < n; i++) {
+        uint8_t *p; int r = surf_ptr(c, sids[i], surfaces[i], &p); if (r) return r;
+        CK(cudaMemcpyAsync(c->out_stage[s] + (size_t)i * c->frame_bytes, p, c->frame_bytes, cudaMemcpyDeviceToDevice, c->st));
+    }
+    CK(cudaEventRecord(c->out_ready[s], c->st));
+    CK(cudaStreamWaitEvent(c->st_d2h, c->out_ready[s], 0));
+    for (int i = 0; i < n; i++)
+        CK(cudaMemcpyAsync(host[i], c->out_stage[s] + (size_t)i * c->frame_bytes, c->frame_bytes, cudaMemcpyDeviceToHost, c->st_d2h));
+    CK(cudaEventRecord(c->out_done[s], c->st_d2h));
+    return 0;
+}
+extern "C" int h264b2_checksum_pictures(H264B2Context *c, int n, const int32_t *sids, const int32_t *surfaces, uint64_t *sums) {
+    if (!c || n < 1 || n > c->n_streams || !sids || !surfaces || !sums) return fail(-1, "checksum_pictures: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st));      // h_ptrs / h_sums are reused
+    for (int i = 0; i < n; i++) { int r = surf_ptr(c, sids[i], surfaces[i], &c->h_ptrs[i]); if (r) return r; }
+    CK(cudaMemcpyAsync(c->d_ptrs, c->h_ptrs, sizeof(uint8_t *) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemsetAsync(c->d_sums, 0, 8 * n, c->st));
+    k_checksum<<<dim3(64, n), 256, 0, c->st>>>(c->d_ptrs, c->frame_bytes / 4, c->d_sums);
+    CK(cudaMemcpyAsync(c->h_sums, c->d_sums, 8 * n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < n; i++) sums[i] = c->h_sums[i];
+    return 0;
+}
+extern "C" int h264b2_checksum_picture(H264B2Context *c, int sid, int surface, uint64_t *sum) {
+    const int32_t s = sid, f = surface;
+    return h264b2_checksum_pictures(c, 1, &s, &f, sum);
+}
+
+// ------------------------------------------------------------------ memory helpers
+extern "C" int h264b2_dev_alloc(H264B2Context *c, size_t bytes, void **p) { if (!c || !p) return fail(-1, "bad argument"); CK(cudaSetDevice(c->device)); CK(cudaMalloc(p, bytes ? bytes : 1)); return 0; }
+extern "C" int h264b2_dev_free(H264B2Context *c, void *p) { if (!c) return fail(-1, "bad argument"); CK(cudaSetDevice(c->device)); CK(cudaFree(p)); return 0; }
+extern "C" int h264b2_dev_upload(H264B2Context *c, void *dst, const void *src, size_t bytes) {
+    if (!c || !dst || !src) return fail(-1, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int h264b2_dev_copy(H264B2Context *c, void *dst, const void *src, size_t bytes) {
+    if (!c || !dst || !src) return fail(-1, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+extern "C" int h264b2_host_alloc(H264B2Context *c, size_t bytes, void **p) { if (!c || !p) return fail(-1, "bad argument"); CK(cudaSetDevice(c->device)); CK(cudaMallocHost(p, bytes ? bytes : 1)); return 0; }
+extern "C" int h264b2_host_free(H264B2Context *c, void *p) { if (!c) return fail(-1, "bad argument"); CK(cudaSetDevice(c->device)); CK(cudaFreeHost(p)); return 0; }
+
+// ------------------------------------------------------------------ timing
+extern "C" int h264b2_timer_start(H264B2Context *c) {
+    if (!c) return fail(-1, "null context");
+    CK(cudaSetDevice(c->device));
+    c->timing = 1; c->ev_used = 0;
+    for (int i = 0; i < KCLASSES; i++) { c->class_ms[i] = 0; c->class_launches[i] = 0; }
+    CK(cudaEventRecord(c->t0, c->st));
+    return 0;
+}
+extern "C" int h264b2_timer_stop(H264B2Context *c, float *ms) {
+    if (!c || !ms) return fail(-1, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st_h2d));
+    for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(c->st, c->out_done[i], 0));   // t1 also covers pending read-backs
+    CK(cudaEventRecord(c->t1, c->st));
+    CK(cudaEventSynchronize(c->t1));
+    CK(cudaStreamSynchronize(c->st_d2h));
+    CK(cudaEventElapsedTime(ms, c->t0, c->t1));
+    for (int i = 0; i + 1 < c->ev_used; i += 2) {
+        float t = 0; CK(cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]));
+        c->class_ms[c->ev_class[i / 2]] += t;
+    }
+    c->timing = 0;
+    return 0;
+}
+extern "C" int h264b2_kernel_times(H264B2Context *c, float *ms5, int64_t *launches) {
+    if (!c || !ms5) return fail(-1, "bad argument");
+    for (int i = 0; i < KCLASSES; i++) { ms5[i] = c->class_ms[i]; if (launches) launches[i] = c->class_launches[i]; }
+    return 0;
+}

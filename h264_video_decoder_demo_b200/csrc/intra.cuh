@@ -1,0 +1,336 @@
+// intra.cuh — intra prediction fused with the intra residual add, run as a
+// macroblock wavefront: one warp owns one MB row (MB-pair row under MBAFF) and advances left to right;
+// before an intra MB at column x it waits until the row above has published progress >= x+2, which
+// covers the left (same warp), top, top-left and top-right neighbours.
+//
+// Reference: Intra_4x4 PB:1062-1419, Intra_8x8 PB:1423-1843 (reference sample filter PB:1536-1599),
+// Intra_16x16 PB:1847-2056, chroma PB:2076-2381 (DC availability uses `> 0`, Q3), I_PCM PB:2449-2499,
+// drivers PB:3401-3929 (block n predicts from block n-1's reconstruction).
+#pragma once
+#include "common.cuh"
+#include "residual.cuh"
+
+struct IntraWarpSmem {
+    ResidualTile rt;
+    int nb[36];
+    int qa[28];
+};
+
+__device__ __forceinline__ int ld_acquire_flag(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_flag(int *p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// ---- 4x4 (nb: [0] corner, [1..4] left y=0..3, [5..12] top x=0..7) ----
+__device__ inline int pred4x4_px(int mode, int x, int y, const int *nb, int &have) {
+#define T(i) ((i) < 0 ? nb[0] : nb[5 + (i)])
+#define L(i) ((i) < 0 ? nb[0] : nb[1 + (i)])
+    const int topok = nb[5] >= 0 && nb[6] >= 0 && nb[7] >= 0 && nb[8] >= 0;
+    const int trok = nb[9] >= 0 && nb[10] >= 0 && nb[11] >= 0 && nb[12] >= 0;
+    const int leftok = nb[1] >= 0 && nb[2] >= 0 && nb[3] >= 0 && nb[4] >= 0;
+    const int cornok = nb[0] >= 0;
+    have = 0;
+    switch (mode) {
+    case 0: if (topok) { have = 1; return T(x); } break;
+    case 1: if (leftok) { have = 1; return L(y); } break;
+    case 2: have = 1;
+        if (topok && leftok) return (T(0)+T(1)+T(2)+T(3)+L(0)+L(1)+L(2)+L(3)+4) >> 3;
+        if (leftok) return (L(0)+L(1)+L(2)+L(3)+2) >> 2;
+        if (topok) return (T(0)+T(1)+T(2)+T(3)+2) >> 2;
+        return 128;
+    case 3: if (topok && trok) { have = 1; return (x == 3 && y == 3) ? (T(6) + 3*T(7) + 2) >> 2 : (T(x+y) + 2*T(x+y+1) + T(x+y+2) + 2) >> 2; } break;
+    case 4: if (topok && leftok && cornok) { have = 1;
+            return x > y ? (T(x-y-2) + 2*T(x-y-1) + T(x-y) + 2) >> 2
+                 : x < y ? (L(y-x-2) + 2*L(y-x-1) + L(y-x) + 2) >> 2
+                 : (T(0) + 2*nb[0] + L(0) + 2) >> 2; } break;
+    case 5: if (topok && leftok && cornok) { have = 1;
+            const int z = 2*x - y;
+            if (z >= 0 && !(z & 1)) return (T(x-(y>>1)-1) + T(x-(y>>1)) + 1) >> 1;
+            if (z >= 0) return (T(x-(y>>1)-2) + 2*T(x-(y>>1)-1) + T(x-(y>>1)) + 2) >> 2;
+            if (z == -1) return (L(0) + 2*nb[0] + T(0) + 2) >> 2;
+            return (L(y-1) + 2*L(y-2) + L(y-3) + 2) >> 2; } break;
+    case 6: if (topok && leftok && cornok) { have = 1;
+            const int z = 2*y - x;
+            if (z >= 0 && !(z & 1)) return (L(y-(x>>1)-1) + L(y-(x>>1)) + 1) >> 1;
+            if (z >= 0) return (L(y-(x>>1)-2) + 2*L(y-(x>>1)-1) + L(y-(x>>1)) + 2) >> 2;
+            if (z == -1) return (L(0) + 2*nb[0] + T(0) + 2) >> 2;
+            return (T(x-1) + 2*T(x-2) + T(x-3) + 2) >> 2; } break;
+    case 7: if (topok && trok) { have = 1;
+            return !(y & 1) ? (T(x+(y>>1)) + T(x+(y>>1)+1) + 1) >> 1 : (T(x+(y>>1)) + 2*T(x+(y>>1)+1) + T(x+(y>>1)+2) + 2) >> 2; } break;
+    case 8: if (leftok) { have = 1;
+            const int z = x + 2*y;
+            if (z <= 4 && !(z & 1)) return (L(y+(x>>1)) + L(y+(x>>1)+1) + 1) >> 1;
+            if (z < 5) return (L(y+(x>>1)) + 2*L(y+(x>>1)+1) + L(y+(x>>1)+2) + 2) >> 2;
+            if (z == 5) return (L(2) + 3*L(3) + 2) >> 2;
+            return L(3); } break;
+    default: break;
+    }
+#undef T
+#undef L
+    return 0;
+}
+
+// ---- 8x8 (qa: filtered samples, [0] corner, [1..8] left y=0..7, [9..24] top x=0..15) ----
+__device__ inline int pred8x8_px(int mode, int x, int y, const int *qa, int &have) {
+#define T(i) ((i) < 0 ? qa[0] : qa[9 + (i)])
+#define L(i) ((i) < 0 ? qa[0] : qa[1 + (i)])
+    int topok = 1, trok = 1, leftok = 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { if (qa[9 + i] < 0) topok = 0; if (qa[17 + i] < 0) trok = 0; if (qa[1 + i] < 0) leftok = 0; }
+    const int cornok = qa[0] >= 0;
+    have = 0;
+    switch (mode) {
+    case 0: if (topok) { have = 1; return T(x); } break;
+    case 1: if (leftok) { have = 1; return L(y); } break;
+    case 2: { have = 1; int v = 0;
+        if (topok && leftok) { for (int i = 0; i < 8; i++) v += T(i) + L(i); return (v + 8) >> 4; }
+        if (leftok) { for (int i = 0; i < 8; i++) v += L(i); return (v + 4) >> 3; }
+        if (topok) { for (int i = 0; i < 8; i++) v += T(i); return (v + 4) >> 3; }
+        return 128; }
+    case 3: if (topok && trok) { have = 1; return (x == 7 && y == 7) ? (T(14) + 3*T(15) + 2) >> 2 : (T(x+y) + 2*T(x+y+1) + T(x+y+2) + 2) >> 2; } break;
+    case 4: if (topok && leftok && cornok) { have = 1;
+            return x > y ? (T(x-y-2) + 2*T(x-y-1) + T(x-y) + 2) >> 2
+                 : x < y ? (L(y-x-2) + 2*L(y-x-1) + L(y-x) + 2) >> 2
+                 : (T(0) + 2*qa[0] + L(0) + 2) >> 2; } break;
+    case 5: if (topok && leftok && cornok) { have = 1;
+            const int z = 2*x - y;
+            if (z >= 0 && !(z & 1)) return (T(x-(y>>1)-1) + T(x-(y>>1)) + 1) >> 1;
+            if (z >= 0) return (T(x-(y>>1)-2) + 2*T(x-(y>>1)-1) + T(x-(y>>1)) + 2) >> 2;
+            if (z == -1) return (L(0) + 2*qa[0] + T(0) + 2) >> 2;
+            return (L(y-2*x-1) + 2*L(y-2*x-2) + L(y-2*x-3) + 2) >> 2; } break;
+    case 6: if (topok && leftok && cornok) { have = 1;
+            const int z = 2*y - x;
+            if (z >= 0 && !(z & 1)) return (L(y-(x>>1)-1) + L(y-(x>>1)) + 1) >> 1;
+            if (z >= 0) return (L(y-(x>>1)-2) + 2*L(y-(x>>1)-1) + L(y-(x>>1)) + 2) >> 2;
+            if (z == -1) return (L(0) + 2*qa[0] + T(0) + 2) >> 2;
+            return (T(x-2*y-1) + 2*T(x-2*y-2) + T(x-2*y-3) + 2) >> 2; } break;
+    case 7: if (topok && trok) { have = 1;
+            return !(y & 1) ? (T(x+(y>>1)) + T(x+(y>>1)+1) + 1) >> 1 : (T(x+(y>>1)) + 2*T(x+(y>>1)+1) + T(x+(y>>1)+2) + 2) >> 2; } break;
+    case 8: if (leftok) { have = 1;
+            const int z = x + 2*y;
+            if (z <= 12 && !(z & 1)) return (L(y+(x>>1)) + L(y+(x>>1)+1) + 1) >> 1;
+            if (z < 13) return (L(y+(x>>1)) + 2*L(y+(x>>1)+1) + L(y+(x>>1)+2) + 2) >> 2;
+            if (z == 13) return (L(6) + 3*L(7) + 2) >> 2;
+            return L(7); } break;
+    default: break;
+    }
+#undef T
+#undef L
+    return 0;
+}
+
+// write one reconstructed sample: pred (or, when the reference would have predicted nothing, what the
+// buffer holds — Q15) + residual, clipped.
+__device__ __forceinline__ void put_px(uint8_t *p, int have, int pred, int res) {
+    if (!have) pred = __ldcg(p);
+    *p = (uint8_t)clip255(pred + res);
+}
+
+// Reconstruct one intra (or I_PCM) macroblock with one warp.
+__device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, int lane, IntraWarpSmem &S) {
+    const int field = P.mbaff && (I.flags & H264B2_MBF_FIELD);
+    const int ys = field ? 2 : 1;
+    int x0, y0;
+    mb_origin(P, a, field, x0, y0);
+    const int W = P.wmb * 16, H = P.hmb * 16, Wc = W >> 1;
+    const int xc0 = x0 >> 1, yc0 = chroma_y0(y0);
+    uint8_t *Y = P.dst, *Cb = P.dst + (size_t)W * H, *Cr = Cb + (size_t)Wc * (H >> 1);
+    const int cls = I.mb_class;
+    if (cls == H264B2_MB_IPCM) {                                       // PB:2449
+        const int16_t *pcm = P.coefs + P.coef_off[a];
+        for (int i = lane; i < 256; i += 32) Y[(size_t)(y0 + ys * (i >> 4)) * W + x0 + (i & 15)] = (uint8_t)pcm[i];
+        for (int i = lane; i < 64; i += 32) {
+            Cb[(size_t)(yc0 + ys * (i >> 3)) * Wc + xc0 + (i & 7)] = (uint8_t)pcm[256 + i];
+            Cr[(size_t)(yc0 + ys * (i >> 3)) * Wc + xc0 + (i & 7)] = (uint8_t)pcm[320 + i];
+        }
+        return;
+    }
+    mb_residual(P, a, I, lane, 32, S.rt, SyncWarp());
+    const int16_t *res = S.rt.res;
+
+    if (cls == H264B2_MB_I16x16) {                                      // PB:1847
+        const int mode = I.pred16_chroma & 3;
+        if (lane < 16) S.nb[1 + lane] = nbr_sample(P, a, lane, -1, 0); else S.nb[17 + lane - 16] = nbr_sample(P, a, -1, lane - 16, 0);
+        if (lane == 0) S.nb[0] = nbr_sample(P, a, -1, -1, 0);
+        __syncwarp();
+        const int *top = S.nb + 1, *left = S.nb + 17;
+        const int corner = S.nb[0];
+        int topok = 1, leftok = 1;
+        for (int i = 0; i < 16; i++) { if (top[i] < 0) topok = 0; if (left[i] < 0) leftok = 0; }
+        int have = 0, dcv = 128, aa = 0, bb = 0, cc = 0;
+        if (mode == 0) have = topok;
+        else if (mode == 1) have = leftok;
+        else if (mode == 2) {
+            have = 1; int v = 0;
+            if (topok && leftok) { for (int i = 0; i < 16; i++) v += top[i] + left[i]; dcv = (v + 16) >> 5; }
+            else if (leftok) { for (int i = 0; i < 16; i++) v += left[i]; dcv = (v + 8) >> 4; }
+            else if (topok) { for (int i = 0; i < 16; i++) v += top[i]; dcv = (v + 8) >> 4; }
+        } else if (topok && leftok) {                                   // the reference does not test p[-1,-1] here (PB:2014-2018)
+            have = 1; int Hh = 0, V = 0;
+            for (int i = 0; i < 8; i++) { Hh += (i + 1) * (top[8 + i] - (6 - i >= 0 ? top[6 - i] : corner)); V += (i + 1) * (left[8 + i] - (6 - i >= 0 ? left[6 - i] : corner)); }
+            aa = 16 * (left[15] + top[15]); bb = (5 * Hh + 32) >> 6; cc = (5 * V + 32) >> 6;
+        }
+        for (int i = lane; i < 256; i += 32) {
+            const int x = i & 15, y = i >> 4;
+            int pred = mode == 0 ? top[x] : mode == 1 ? left[y] : mode == 2 ? dcv : clip255((aa + bb * (x - 7) + cc * (y - 7) + 16) >> 5);
+            put_px(&Y[(size_t)(y0 + y * ys) * W + x0 + x], have, pred, res[y * 16 + x]);
+        }
+    } else if (cls == H264B2_MB_I8x8) {                                 // PB:1423, PB:3651
+        const uint64_t modes = P.modes[a];
+        for (int b = 0; b < 4; b++) {
+            const int mode = (int)((modes >> (4 * b)) & 15);
+            const int xO = (b & 1) * 8, yO = (b >> 1) * 8;
+            if (lane < 9) S.nb[lane] = nbr_sample(P, a, xO - 1, yO + lane - 1, 0);
+            else if (lane < 25) S.nb[lane] = nbr_sample(P, a, xO + lane - 9, yO - 1, 0);
+            __syncwarp();
+            {   // top-right substitution, then reference sample filtering 8.3.2.2.1 (PB:1536-1599); every lane computes one qa[]
+                int trmiss = 1;
+                for (int x = 8; x < 16; x++) if (S.nb[9 + x] >= 0) trmiss = 0;
+                const int sub = trmiss && S.nb[9 + 7] >= 0;
+#define PT(i) ((i) >= 8 && sub ? S.nb[9 + 7] : S.nb[9 + (i)])
+#define PL(i) (S.nb[1 + (i)])
+                const int pc = S.nb[0];
+                int top16 = 1, left8 = 1;
+                for (int x = 0; x < 16; x++) if (PT(x) < 0) top16 = 0;
+                for (int y = 0; y < 8; y++) if (PL(y) < 0) left8 = 0;
+                int v = -1;
+                if (lane == 0) {
+                    if (pc >= 0) {
+                        if (PT(0) < 0 || PL(0) < 0) { v = PT(0) >= 0 ? (3*pc + PT(0) + 2) >> 2 : PL(0) >= 0 ? (3*pc + PL(0) + 2) >> 2 : pc; }
+                        else v = (PT(0) + 2*pc + PL(0) + 2) >> 2;
+                    }
+                } else if (lane < 9) {
+                    const int y = lane - 1;
+                    if (left8) v = y == 0 ? (pc >= 0 ? (pc + 2*PL(0) + PL(1) + 2) >> 2 : (3*PL(0) + PL(1) + 2) >> 2)
+                                 : y == 7 ? (PL(6) + 3*PL(7) + 2) >> 2 : (PL(y-1) + 2*PL(y) + PL(y+1) + 2) >> 2;
+                } else if (lane < 25) {
+                    const int x = lane - 9;
+                    if (top16) v = x == 0 ? (pc >= 0 ? (pc + 2*PT(0) + PT(1) + 2) >> 2 : (3*PT(0) + PT(1) + 2) >> 2)
+                                 : x == 15 ? (PT(14) + 3*PT(15) + 2) >> 2 : (PT(x-1) + 2*PT(x) + PT(x+1) + 2) >> 2;
+                }
+#undef PT
+#undef PL
+                if (lane < 25) S.qa[lane] = v;
+            }
+            __syncwarp();
+            for (int i = lane; i < 64; i += 32) {
+                const int x = i & 7, y = i >> 3;
+                int have; const int pred = pred8x8_px(mode, x, y, S.qa, have);
+                put_px(&Y[(size_t)(y0 + (yO + y) * ys) * W + x0 + xO + x], have, pred, res[(yO + y) * 16 + xO + x]);
+            }
+            __syncwarp();
+        }
+    } else {                                                            // Intra_4x4: PB:1062, PB:3401
+        const uint64_t modes = P.modes[a];
+        for (int b = 0; b < 16; b++) {
+            const int mode = (int)((modes >> (4 * b)) & 15);
+            const int xO = blk_x(b), yO = blk_y(b);
+            if (lane < 5) S.nb[lane] = nbr_sample(P, a, xO - 1, yO + lane - 1, 0);
+            else if (lane < 13) { const int x = lane - 5; S.nb[lane] = (x > 3 && (b == 3 || b == 11)) ? -1 : nbr_sample(P, a, xO + x, yO - 1, 0); }
+            __syncwarp();
+            if (lane == 0 && S.nb[9] < 0 && S.nb[10] < 0 && S.nb[11] < 0 && S.nb[12] < 0 && S.nb[8] >= 0) { S.nb[9] = S.nb[10] = S.nb[11] = S.nb[12] = S.nb[8]; }
+            __syncwarp();
+            if (lane < 16) {
+                const int x = lane & 3, y = lane >> 2;
+                int have; const int pred = pred4x4_px(mode, x, y, S.nb, have);
+                put_px(&Y[(size_t)(y0 + (yO + y) * ys) * W + x0 + xO + x], have, pred, res[(yO + y) * 16 + xO + x]);
+            }
+            __syncwarp();
+        }
+    }
+
+    // chroma, both components (PB:2076)
+    const int cmode = (I.pred16_chroma >> 2) & 3;
+    for (int comp = 1; comp <= 2; comp++) {
+        __syncwarp();
+        if (lane < 8) S.nb[1 + lane] = nbr_sample(P, a, lane, -1, comp);
+        else if (lane < 16) S.nb[9 + lane - 8] = nbr_sample(P, a, -1, lane - 8, comp);
+        else if (lane == 16) S.nb[0] = nbr_sample(P, a, -1, -1, comp);
+        __syncwarp();
+        const int *top = S.nb + 1, *left = S.nb + 9;
+        const int corner = S.nb[0];
+        uint8_t *pl = comp == 1 ? Cb : Cr;
+        const int16_t *cres = res + 256 + (comp - 1) * 64;
+        int topok = 1, leftok = 1;
+        for (int i = 0; i < 8; i++) { if (top[i] < 0) topok = 0; if (left[i] < 0) leftok = 0; }
+        int have = 0, aa = 0, bb = 0, cc = 0;
+        if (cmode == 0) have = 1;
+        else if (cmode == 1) have = leftok;
+        else if (cmode == 2) have = topok;
+        else if (topok && leftok && corner >= 0) {
+            have = 1; int Hh = 0, V = 0;
+            for (int i = 0; i < 4; i++) { Hh += (i + 1) * (top[4 + i] - (2 - i >= 0 ? top[2 - i] : corner)); V += (i + 1) * (left[4 + i] - (2 - i >= 0 ? left[2 - i] : corner)); }
+            aa = 16 * (left[7] + top[7]); bb = (34 * Hh + 32) >> 6; cc = (34 * V + 32) >> 6;
+        }
+        for (int i = lane; i < 64; i += 32) {
+            const int x = i & 7, y = i >> 3;
+            int pred;
+            if (cmode == 0) {
+                const int xO = x & 4, yO = y & 4;
+                // `> 0`: a neighbouring sample equal to 0 counts as unavailable (Q3, PB:2205-2250)
+                const int t = top[xO] > 0 && top[xO+1] > 0 && top[xO+2] > 0 && top[xO+3] > 0;
+                const int l = left[yO] > 0 && left[yO+1] > 0 && left[yO+2] > 0 && left[yO+3] > 0;
+                const int st = top[xO] + top[xO+1] + top[xO+2] + top[xO+3], sl = left[yO] + left[yO+1] + left[yO+2] + left[yO+3];
+                if ((xO == 0 && yO == 0) || (xO > 0 && yO > 0)) pred = (t && l) ? (st + sl + 4) >> 3 : l ? (sl + 2) >> 2 : t ? (st + 2) >> 2 : 128;
+                else if (xO > 0) pred = t ? (st + 2) >> 2 : l ? (sl + 2) >> 2 : 128;
+                else pred = l ? (sl + 2) >> 2 : t ? (st + 2) >> 2 : 128;
+            } else if (cmode == 1) pred = left[y];
+            else if (cmode == 2) pred = top[x];
+            else pred = clip255((aa + bb * (x - 3) + cc * (y - 3) + 16) >> 5);
+            put_px(&pl[(size_t)(yc0 + y * ys) * Wc + xc0 + x], have, pred, cres[y * 8 + x]);
+        }
+    }
+    __syncwarp();
+}
+
+// Wavefront driver.  ticket: one counter per launch (zeroed by the host); tickets are handed out
+// picture-interleaved so that every row's dependency (same picture, row-1) holds a smaller ticket and
+// is therefore already resident or finished: no deadlock regardless of how CTAs are scheduled.
+__global__ void __launch_bounds__(128) k_intra(const PicDev *pics, int npics, int max_rows, int *ticket) {
+    __shared__ IntraWarpSmem sm[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= npics * max_rows) return;
+    const PicDev &P = pics[t % npics];
+    const int row = t / npics;
+    const int per = P.mbaff ? 2 : 1;
+    const int rows = P.hmb / per, wmb = P.wmb;
+    if (row >= rows) return;
+    int *prog = P.progress;             // [0][row]
+    int seen = row == 0 ? wmb : 0;
+    for (int xb = 0; xb < wmb; xb += 32) {
+        const int xl = xb + lane;
+        int intra_here = 0;
+        if (xl < wmb) for (int s = 0; s < per; s++) { const int c = P.info[(row * wmb + xl) * per + s].mb_class; intra_here |= (c >= H264B2_MB_I4x4 && c <= H264B2_MB_IPCM); }
+        unsigned mask = __ballot_sync(0xffffffffu, intra_here);
+        while (mask) {
+            const int x = xb + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int need = min(x + 2, wmb);
+            if (seen < need) {
+                if (lane == 0) {
+                    st_relaxed_flag(&prog[row], x);          // everything left of x is final: let the row below run on
+                    while ((seen = ld_acquire_flag(&prog[row - 1])) < need) __nanosleep(20);
+                }
+                seen = __shfl_sync(0xffffffffu, seen, 0);
+                __threadfence();
+            }
+            for (int s = 0; s < per; s++) {
+                const int a = (row * wmb + x) * per + s;
+                const H264B2MbInfo I = P.info[a];
+                if (I.mb_class >= H264B2_MB_I4x4 && I.mb_class <= H264B2_MB_IPCM) intra_mb(P, a, I, lane, sm[warp]);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_relaxed_flag(&prog[row], x + 1);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) st_relaxed_flag(&prog[row], wmb);
+}

@@ -142,8 +142,10 @@ int h264b2_destroy(H264B2Context *ctx);
 
 /* Reconstruct one picture per listed stream (pictures of one stream are serial;
  * pictures of different streams run concurrently in one launch sequence).
- * Host arrays are copied to the device asynchronously from pinned staging;
- * the call returns after enqueueing.  stream_ids[i] in [0, n_streams). */
+ * Host arrays are DMA'd to the device asynchronously on a copy stream (one transfer per contiguous
+ * span; pictures whose arrays lie back to back need one transfer) into a 3-deep device arena, so the
+ * copy of batch k+1 overlaps the kernels of batch k.  The call returns after enqueueing; the host
+ * arrays must stay valid until h264b2_sync() or until 3 further submits have been issued.  stream_ids[i] in [0, n_streams). */
 int h264b2_submit(H264B2Context *ctx, int n_pics, const int32_t *stream_ids,
                   const H264B2PicParams *pics);
 
@@ -156,12 +158,22 @@ int h264b2_submit_device(H264B2Context *ctx, int n_pics, const int32_t *stream_i
  * Synchronises with all prior work on the context. */
 int h264b2_read_picture(H264B2Context *ctx, int stream_id, int surface, uint8_t *host_i420);
 
+/* Asynchronous read-back of n surfaces (one per listed stream, n <= n_streams) into host memory
+ * (pinned memory from h264b2_host_alloc gives true overlap): the surfaces are snapshotted on the launch
+ * stream, then drained over PCIe on a separate stream, so the next submit does not wait for the copy.
+ * host[i] is complete after h264b2_sync().  This is what the output callback path uses: the reference hands
+ * the callback a host picture (H264VideoDecoder.cpp:118, 396-432). */
+int h264b2_read_pictures_async(H264B2Context *ctx, int n, const int32_t *stream_ids, const int32_t *surfaces,
+                               uint8_t *const *host_i420);
+
 /* Write a surface from host I420 (used by tests to seed reference pictures). */
 int h264b2_write_picture(H264B2Context *ctx, int stream_id, int surface, const uint8_t *host_i420);
 
 /* 64-bit positional checksum of a surface computed on the GPU (the only data
  * that has to leave the GPU in the multi-stream/multi-GPU configuration). */
 int h264b2_checksum_picture(H264B2Context *ctx, int stream_id, int surface, uint64_t *checksum);
+
+int h264b2_checksum_pictures(H264B2Context *ctx, int n, const int32_t *stream_ids, const int32_t *surfaces, uint64_t *checksums);
 
 /* Device pointer of a surface (Y plane; Cb = Y + W*H, Cr = Cb + W*H/4). */
 int h264b2_surface_ptr(H264B2Context *ctx, int stream_id, int surface, void **dev_ptr);
@@ -170,6 +182,10 @@ int h264b2_surface_ptr(H264B2Context *ctx, int stream_id, int surface, void **de
 int h264b2_dev_alloc(H264B2Context *ctx, size_t bytes, void **dev_ptr);
 int h264b2_dev_free(H264B2Context *ctx, void *dev_ptr);
 int h264b2_dev_upload(H264B2Context *ctx, void *dev_dst, const void *host_src, size_t bytes);
+int h264b2_dev_copy(H264B2Context *ctx, void *dev_dst, const void *dev_src, size_t bytes);
+/* Page-locked host memory: SoA buffers the host entropy stage fills here are DMA'd by h264b2_submit without a staging copy. */
+int h264b2_host_alloc(H264B2Context *ctx, size_t bytes, void **host_ptr);
+int h264b2_host_free(H264B2Context *ctx, void *host_ptr);
 
 /* Block until all enqueued work is done. */
 int h264b2_sync(H264B2Context *ctx);
@@ -177,7 +193,8 @@ int h264b2_sync(H264B2Context *ctx);
 /* Event timing on the context's launch stream (CUDA events; for bench.py). */
 int h264b2_timer_start(H264B2Context *ctx);
 int h264b2_timer_stop(H264B2Context *ctx, float *elapsed_ms);
-/* Per-kernel-class accumulated time of the last timed region (ms): [clear, residual+inter, intra, bs, deblock]. */
+/* Per-kernel-class accumulated device time (ms) and launch counts of the last timed region:
+ * [0] clears/memsets, [1] k_inter (MC + inter residual), [2] k_intra, [3] k_bs, [4] k_deblock. */
 int h264b2_kernel_times(H264B2Context *ctx, float *ms5, int64_t *launches);
 
 /* ABI version / last error string (static storage). */

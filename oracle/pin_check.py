@@ -33,7 +33,7 @@ def check(path, max_pictures=None):
 
 
 if __name__ == "__main__":
-    files = sys.argv[1:] or sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "replay", "*.bin")))
+    files = sys.argv[1:] or sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "replay", "*.bin.xz")))
     with ProcessPoolExecutor(max_workers=min(8, len(files))) as ex:
         for name, n, bad, out_ok, dt in ex.map(check, files):
             print(f"{name}: {n} pictures, mismatches={bad[:8]}{'...' if len(bad) > 8 else ''} ({len(bad)}), output-order sums ok={out_ok}, {dt:.1f}s")
