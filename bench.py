@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — 1080p pictures/s of the B200 H.264 picture-reconstruction engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--workload NAME] [--impl reference]
+
+A "step" is one pass of the hot path over one whole bundled stream for S concurrent replicas on every GPU:
+76 batched submits (one per picture in decoding order; pictures of one stream are serial), each
+reconstructing S pictures.  Inputs are the per-picture structure-of-arrays that the host entropy stage
+emits (pre-parsed by the unmodified reference's own parser through oracle/ref_harness), made resident in
+HBM before the timed region — one distinct device copy per replica, 16 GB at S=64, far larger than L2.
+
+  value     pictures/s, device-timed (CUDA events on the launch stream), inputs resident in HBM
+  e2e       pictures/s through h264b2_submit() with HOST (pinned) buffers: H2D of every picture's SoA and D2H
+            of every reconstructed picture (what the reference's output callback receives) inside the region
+  roofline  dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the unmodified reference decoder (oracle/_ref/ref_harness) on one host core, bounded sample
+
+--impl reference times the reference's own CPU decoder on all usable host cores (one process per core).
+Multi-GPU (torchrun, one rank per GPU): streams shard with no data-path collective; weak scaling.
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "1080p frames/sec decoded (picture reconstruction), YUV bit-exact vs reference"
+UNIT = "frames/s"
+WORKLOADS = {
+    "B_frames.cabac": "HeavyHand_1080p.B_frames.cabac",
+    "B_frames_4.no_cabac": "HeavyHand_1080p.B_frames_4.no_cabac.no_tff",
+    "tff": "HeavyHand_1080p.B_frames_cabac_tff",
+    "no_B_frames.cabac": "HeavyHand_1080p.no_B_frames.cabac.no_tff",
+    "gop121": "gop121.naluCnt453",
+}
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def find_replay(stem):
+    full = os.path.join(REF_DIR, "replay", stem + ".bin.xz")
+    if os.path.exists(full):
+        return full, True
+    gd = os.path.join(ROOT, "tests", "golden")
+    for f in sorted(os.listdir(gd)):
+        if f.startswith(stem + ".first"):
+            return os.path.join(gd, f), False
+    raise FileNotFoundError(f"no replay container for {stem}")
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v == "Active":
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference CPU decoder
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_once(stream_stem, max_frames, nproc):
+    """nproc single-threaded reference decoders in parallel, each decoding the first pictures of the stream until
+    max_frames frames have reached the output callback.  Returns (pictures decoded in total, wall seconds)."""
+    exe = os.path.join(REF_DIR, "ref_harness")
+    src = os.path.join(REF_DIR, "streams", stream_stem + ".h264")
+    if not (os.path.exists(exe) and os.path.exists(src)):
+        return None
+    t0 = time.time()
+    procs = [subprocess.Popen([exe, src, "--max-frames", str(max_frames), "--quiet"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+             for _ in range(nproc)]
+    pics = 0
+    for p in procs:
+        _, err = p.communicate()
+        m = re.search(r"RESULT .*frames=(\d+) pics=(\d+) secs=([\d.]+)", err or "")
+        if m:
+            pics += int(m.group(2))
+    return pics, time.time() - t0
+
+
+def reference_arm(args, stem):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not os.path.exists(os.path.join(REF_DIR, "ref_harness")):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness not built (needs /root/reference at build time)"}))
+        return
+    cores = usable_cores()
+    try:
+        avail_gb = int(re.search(r"MemAvailable:\s+(\d+)", open("/proc/meminfo").read()).group(1)) / 1048576
+    except Exception:
+        avail_gb = 16
+    nproc = max(1, min(cores, int(avail_gb * 0.5 / 1.5), 64))       # ~1 GB RSS per decoder on a short sample
+    total_steps = args.steps + args.warmup
+    frames = max(3, min(10, int(150.0 / max(total_steps, 1) * 1.2)))   # keep the whole run to a few minutes
+    for _ in range(args.warmup):
+        run_reference_once(stem, frames, nproc)
+    pics, secs = 0, 0.0
+    for _ in range(args.steps):
+        p, s = run_reference_once(stem, frames, nproc)
+        pics += p; secs += s
+    v = pics / secs
+    sample = f"{nproc} parallel single-threaded reference decoders x first {frames} output frames of {stem}.h264 per step (process start-up included)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1000 * secs / max(args.steps, 1), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "bundled reference bitstream", "config": {"workload": stem + ".h264 (reference CPU decoder, all usable host cores)"},
+        "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------ algorithmic bytes
+def algorithmic_bytes(rp):
+    """Per picture: MC = 24 B x (nLists + 1) per inter 4x4 luma block (16 Y + 4 Cb + 4 Cr read once per list,
+    written once); deblock = every sample of a deblocked picture read + written once; intra = samples written."""
+    import numpy as np
+    from h264_video_decoder_demo_b200 import abi
+    out = []
+    for p in rp.pictures:
+        mc = 0
+        if p.motion is not None:
+            inter = p.mb_info["mb_class"] == abi.MB_INTER
+            lists = (p.motion["ref_surf"][inter] >= 0).sum(axis=1)      # [n_inter][4 quadrants] -> lists per quadrant
+            mc = int((4 * 24 * (lists + 1)).sum())
+        intra = int(((p.mb_info["mb_class"] >= abi.MB_I4x4) & (p.mb_info["mb_class"] <= abi.MB_IPCM)).sum()) * 384
+        dbk = 2 * rp.frame_bytes if p.deblock_enable else 0
+        out.append({"inter": mc, "intra": intra, "deblock": dbk})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=64, help="concurrent replicas of the stream per GPU")
+    ap.add_argument("--workload", default="B_frames.cabac", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--max-pictures", type=int, default=None)
+    args = ap.parse_args()
+    stem = WORKLOADS[args.workload]
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        import socket
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    if args.impl == "reference":
+        reference_arm(args, stem)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import numpy as np
+    from h264_video_decoder_demo_b200 import engine, replay, sharding
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    path, is_full = find_replay(stem)
+    S = args.streams
+    eng_probe = engine.load_library()   # fails loudly when the CUDA library is missing: no fallback
+    del eng_probe
+    raw = replay.read_replay_bytes(path)
+    rp0 = replay.parse_replay(raw, path, args.max_pictures)
+    eng = engine.Engine(local_rank, S, rp0.width_mbs, rp0.height_mbs)
+    # page-locked copy of the container: the e2e leg DMAs every picture's arrays straight from it
+    pinned = eng.pinned_array(len(raw))
+    pinned[:] = np.frombuffer(raw, dtype=np.uint8)
+    del raw
+    rp = replay.parse_replay(pinned, path, args.max_pictures)
+    npic = len(rp.pictures)
+    # resident replicas: one distinct HBM copy of the SoA per stream
+    rs = [engine.ResidentStream(eng, rp)]
+    for _ in range(1, S):
+        rs.append(rs[0].clone())
+    sids = list(range(S))
+    batches = [eng.prepare(sids, [rs[s].params[i] for s in sids]) for i in range(npic)]
+    host_params = [replay.pic_params(rp, pic) for pic in rp.pictures]
+    host_batches = [eng.prepare(sids, [host_params[i]] * S) for i in range(npic)]
+    dst = [pic.dst_surface for pic in rp.pictures]
+
+    def step():
+        for b in batches:
+            eng.submit_prepared(b)
+
+    # ---- warm-up (the last warm-up step is checked against the reference's checksums, every stream, every picture)
+    for w in range(max(args.warmup, 1)):
+        if w == max(args.warmup, 1) - 1:
+            for i, b in enumerate(batches):
+                eng.submit_prepared(b)
+                sums = eng.checksums(sids, [dst[i]] * S)
+                if any(x != rp.pictures[i].sum_post for x in sums):
+                    raise SystemExit(f"PARITY FAILURE: picture {i}: {sum(x != rp.pictures[i].sum_post for x in sums)} of {S} streams differ from the reference")
+        else:
+            step()
+    eng.sync()
+
+    # ---- timed region: device time by CUDA events on the launch stream, max over ranks
+    sampler = ClockSampler(local_rank)
+    time.sleep(0.3)
+    sharding.barrier()
+    eng.sync()
+    t_wall0 = time.time()
+    eng.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = eng.timer_stop()
+    t_wall1 = time.time()
+    sharding.barrier()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    kt = eng.kernel_times()
+    ms_max = sharding.max_over_ranks(ms)
+    pictures_per_rank = S * npic * args.steps
+    value = pictures_per_rank * world / (ms_max / 1000.0)
+    # final state check: the last picture of every stream still equals the reference
+    sums = eng.checksums(sids, [dst[-1]] * S)
+    if any(x != rp.pictures[-1].sum_post for x in sums):
+        raise SystemExit("PARITY FAILURE after the timed region")
+
+    # ---- roofline of the dominant kernel
+    ab = algorithmic_bytes(rp)
+    per_step = {k: sum(a[k] for a in ab) * S for k in ("inter", "intra", "deblock")}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(("inter", "intra", "deblock"), key=lambda k: kt[k]["ms"])
+    dom_ms = kt[dom]["ms"] + (kt["bs"]["ms"] if dom == "deblock" else 0.0)
+    kernels = {}
+    for k in ("inter", "intra", "deblock"):
+        t = kt[k]["ms"] + (kt["bs"]["ms"] if k == "deblock" else 0.0)
+        kernels[k] = {"ms_per_step": round(t / args.steps, 3), "launches_per_step": kt[k]["launches"] // max(args.steps, 1),
+                      "algorithmic_gb_per_step": round(per_step[k] / 1e9, 4),
+                      "achieved_gbs": round(per_step[k] * args.steps / (t / 1000.0) / 1e9, 1) if t > 0 else None}
+    achieved = kernels[dom]["achieved_gbs"]
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get({"inter": "k_inter", "intra": "k_intra", "deblock": "k_deblock"}[dom], {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": {"inter": "k_inter", "intra": "k_intra", "deblock": "k_bs+k_deblock"}[dom], "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": round(dom_ms / ms, 3), "kernels": kernels}
+    launches = sum(kt[k]["launches"] for k in ("inter", "intra", "bs", "deblock"))
+
+    # ---- e2e: host buffers in, host pictures out, through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        nbuf = 2
+        out_host = [eng.pinned_array(S * eng.frame_bytes) for _ in range(nbuf)]
+        out_ptrs = [[int(o.ctypes.data) + s * eng.frame_bytes for s in sids] for o in out_host]
+
+        def e2e_step():
+            for i, b in enumerate(host_batches):
+                eng.submit_prepared_host(b)
+                eng.read_pictures_async(sids, [dst[i]] * S, out_ptrs[i % nbuf])
+
+        e2e_step()
+        eng.sync()
+        # the frames that came back are the reference's frames
+        last = (npic - 1) % nbuf
+        from h264_video_decoder_demo_b200 import abi
+        for s in (0, S - 1):
+            if abi.checksum(out_host[last][s * eng.frame_bytes:(s + 1) * eng.frame_bytes].tobytes()) != rp.pictures[-1].sum_post:
+                raise SystemExit("PARITY FAILURE in the e2e path")
+        sharding.barrier()
+        t0 = time.time()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        eng.sync()
+        t1 = sharding.max_over_ranks(time.time() - t0)
+        e2e = {"value": round(S * npic * args.e2e_steps * world / t1, 1), "unit": UNIT,
+               "h2d_bytes_per_step": int(sum(p.nbytes() for p in rp.pictures) * S), "d2h_bytes_per_step": int(npic * S * eng.frame_bytes),
+               "steps": args.e2e_steps, "timing": "host wall clock around submit+read-back of every picture, synchronised on both sides, max over ranks"}
+
+    # ---- CPU baseline: the unmodified reference on one host core (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = run_reference_once(stem, 16, 1)
+        if r:
+            cpu = {"value": round(r[0] / r[1], 3), "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"oracle/_ref/ref_harness (unmodified reference, its Makefile flags) on {stem}.h264 until 16 frames reached the callback: {r[0]} pictures in {r[1]:.1f} s"}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref/ref_harness not present on this box"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "bundled reference bitstream pre-parsed by the reference's own parser (SoA resident in HBM)",
+            "config": {"workload": f"{stem}.h264 x {S} concurrent replicas per GPU" + ("" if is_full else " (golden prefix only: full replay not built)"),
+                       "pictures_per_step_per_gpu": S * npic, "streams_per_gpu": S, "picture": "1920x1088 I420",
+                       "l2": "inputs larger than L2: one distinct SoA copy + 17-surface DPB per replica (%.1f GB per GPU)" % ((sum(rs[0].blob_bytes) + 17 * eng.frame_bytes) * S / 1e9),
+                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

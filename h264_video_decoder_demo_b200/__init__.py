@@ -4,4 +4,4 @@ The product is the CUDA library behind include/h264_recon_b200.h; this package h
 sources (csrc/), the ctypes mirror of the ABI, the host-side mirror of the reference's
 decoder interface and the replay-file reader.  Nothing here imports oracle/.
 """
-from . import abi, replay  # noqa: F401
+from . import abi, replay, sharding  # noqa: F401

@@ -45,7 +45,7 @@ __global__ void k_checksum(const uint8_t *const *surf, size_t nwords, unsigned l
 }
 
 // ------------------------------------------------------------------ context
-enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 8192, KCLASSES = 5 };
+enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 5 };
 
 struct H264B2Context {
     int device, n_streams, spp, wmb, hmb, nmb;

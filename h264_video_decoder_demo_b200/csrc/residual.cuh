@@ -17,6 +17,10 @@ struct ResidualTile {
     int     dcC[2][4];     // chroma DC after the 2x2 Hadamard
 };
 
+// Residuals are stored as int16.  The reference keeps them in int32 and only ever uses them in
+// Clip1(pred + r) with pred in [0,255], so saturating r to +-4096 cannot change any output sample.
+__device__ __forceinline__ int16_t sat_res(int v) { return (int16_t)min(max(v, -4096), 4096); }
+
 // 4x4 block owned by one thread.  lv: 16 list-order levels or nullptr; dc_pass: position 0 takes dcval as is.
 __device__ inline void resid4x4_thread(const int16_t *lv, int dcval, int dc_pass, int qp, const int16_t *ls /*[6][16]*/,
                                        int field, int16_t *out, int ostride) {
@@ -43,10 +47,10 @@ __device__ inline void resid4x4_thread(const int16_t *lv, int dcval, int dc_pass
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int g0 = f[j] + f[8+j], g1 = f[j] - f[8+j], g2 = (f[4+j] >> 1) - f[12+j], g3 = f[4+j] + (f[12+j] >> 1);
-        out[0*ostride + j] = (int16_t)((g0 + g3 + 32) >> 6);
-        out[1*ostride + j] = (int16_t)((g1 + g2 + 32) >> 6);
-        out[2*ostride + j] = (int16_t)((g1 - g2 + 32) >> 6);
-        out[3*ostride + j] = (int16_t)((g0 - g3 + 32) >> 6);
+        out[0*ostride + j] = sat_res((g0 + g3 + 32) >> 6);
+        out[1*ostride + j] = sat_res((g1 + g2 + 32) >> 6);
+        out[2*ostride + j] = sat_res((g1 - g2 + 32) >> 6);
+        out[3*ostride + j] = sat_res((g0 - g3 + 32) >> 6);
     }
 }
 
@@ -74,7 +78,7 @@ __device__ inline void resid8x8_thread(const int16_t *lv, int qp, const int16_t 
     for (int j = 0; j < 8; j++) {
         butterfly8(d[j], d[8+j], d[16+j], d[24+j], d[32+j], d[40+j], d[48+j], d[56+j]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) out[i * ostride + j] = (int16_t)((d[8*i+j] + 32) >> 6);
+        for (int i = 0; i < 8; i++) out[i * ostride + j] = sat_res((d[8*i+j] + 32) >> 6);
     }
 }
 

@@ -80,7 +80,17 @@ def _read_all(path: str) -> bytes:
 
 
 def load_replay(path: str, max_pictures: Optional[int] = None) -> Replay:
-    buf = _read_all(path)
+    return parse_replay(_read_all(path), path, max_pictures)
+
+
+def read_replay_bytes(path: str) -> bytes:
+    """Raw (decompressed) container bytes, e.g. to place them in page-locked memory before parsing."""
+    return _read_all(path)
+
+
+def parse_replay(buf, path: str = "<buffer>", max_pictures: Optional[int] = None) -> Replay:
+    """Parse a container held in any buffer object; the numpy arrays are VIEWS into `buf` (so a pinned
+    buffer yields pinned, per-picture contiguous arrays that h264b2_submit can DMA in one transfer)."""
     magic, version, wmb, hmb, n_pics, n_out, hdr_bytes, pichdr_bytes, _ = _FILE_HDR.unpack_from(buf, 0)
     if magic != b"H264B2RP" or version != 1:
         raise ValueError(f"{path}: not a replay file")
@@ -142,3 +152,32 @@ def pic_params(rp: Replay, pic: Picture, ptrs=None) -> PicParams:
 
 def default_replay_dir() -> str:
     return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "replay")
+
+
+def save_replay(rp: Replay, path: str, n_pictures: Optional[int] = None, preset: int = 6) -> None:
+    """Write the first n_pictures (decoding order) of `rp` as a replay container (xz if path ends with .xz)."""
+    pics = rp.pictures[:n_pictures] if n_pictures is not None else rp.pictures
+    keep = {p.decode_idx for p in pics}
+    outs = [(i, s) for i, s in zip(rp.out_order, rp.out_sums) if i in keep]
+    parts = [_FILE_HDR.pack(b"H264B2RP", 1, rp.width_mbs, rp.height_mbs, len(pics), len(outs), _FILE_HDR.size, _PIC_HDR.size, 0)]
+    for p in pics:
+        parts.append(_PIC_HDR.pack(p.decode_idx, p.dst_surface, p.clear_surface, p.has_inter, p.deblock_enable, p.deblock_stop_mb,
+                                   p.mbaff, p.cqp[0], p.cqp[1], len(p.weights), 1 if p.level_scale4 is not None else 0,
+                                   p.slice_type, p.poc, p.n_na, len(p.coefs), p.nal_ref_idc, p.sum_pre, p.sum_post))
+        parts += [p.mb_info.tobytes(), p.intra_modes.tobytes(), p.coef_offset.tobytes()]
+        if p.has_inter:
+            parts.append(p.motion.tobytes())
+        parts += [p.weights.tobytes(), p.coefs.tobytes()]
+        if p.level_scale4 is not None:
+            parts += [p.level_scale4.tobytes(), p.level_scale8.tobytes()]
+    out = np.zeros(len(outs), dtype=np.dtype([("idx", "<i4"), ("pad", "<i4"), ("sum", "<u8")]))
+    out["idx"] = [i for i, _ in outs]
+    out["sum"] = [s for _, s in outs]
+    parts.append(out.tobytes())
+    blob = b"".join(parts)
+    if path.endswith(".xz"):
+        with lzma.open(path, "wb", preset=preset) as f:
+            f.write(blob)
+    else:
+        with open(path, "wb") as f:
+            f.write(blob)

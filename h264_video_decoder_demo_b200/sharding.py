@@ -1,0 +1,63 @@
+"""Multi-GPU partitioning: independent bitstreams (or closed GOPs) are dealt round-robin to ranks.
+
+The path shards with NO data-path collective: every rank owns its streams' decoded picture
+buffers; the only cross-rank traffic is the 8-byte frame checksums and the timing max, carried by
+torch.distributed (NCCL on the GPU box, gloo in the CPU tests)."""
+from typing import Dict, List
+
+
+def shard(n_units: int, rank: int, world: int) -> List[int]:
+    """Unit i (stream or GOP index) -> rank i % world."""
+    return list(range(rank, n_units, world))
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def _device():
+    import torch
+    d = _dist()
+    if d is not None and d.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_checksums(local: Dict[int, int], n_units: int) -> List[int]:
+    """All ranks contribute {unit: u64 checksum}; returns the full list on every rank."""
+    import torch
+    d = _dist()
+    # two int32 halves per checksum: exact under SUM on every backend
+    t = torch.zeros(n_units, 2, dtype=torch.int64, device=_device())
+    for u, s in local.items():
+        t[u, 0] = s & 0xFFFFFFFF
+        t[u, 1] = (s >> 32) & 0xFFFFFFFF
+    if d is not None and d.get_world_size() > 1:
+        d.all_reduce(t, op=d.ReduceOp.SUM)
+    t = t.cpu()
+    return [int(t[u, 0]) | (int(t[u, 1]) << 32) for u in range(n_units)]
+
+
+def max_over_ranks(value: float) -> float:
+    import torch
+    d = _dist()
+    t = torch.tensor([value], dtype=torch.float64, device=_device())
+    if d is not None and d.get_world_size() > 1:
+        d.all_reduce(t, op=d.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float) -> float:
+    import torch
+    d = _dist()
+    t = torch.tensor([value], dtype=torch.float64, device=_device())
+    if d is not None and d.get_world_size() > 1:
+        d.all_reduce(t, op=d.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier():
+    d = _dist()
+    if d is not None and d.get_world_size() > 1:
+        d.barrier()

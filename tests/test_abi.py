@@ -1,0 +1,79 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, and the Python mirrors of the structs match the C layout byte for byte."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from h264_video_decoder_demo_b200 import abi, engine
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "h264_recon_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(h264b2_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = engine.load_library()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"libh264b2.so does not export {s}"
+    assert set(syms) == set(engine.ABI_SYMBOLS), "engine.py prototypes and the header disagree"
+    assert lib.h264b2_abi_version() == abi.ABI_VERSION
+
+
+def test_struct_layouts_match_c():
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "h264_recon_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu\n", sizeof(H264B2MbInfo), sizeof(H264B2MbMotion), sizeof(H264B2Weight), sizeof(H264B2PicParams));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(H264B2MbInfo, qpy), offsetof(H264B2MbInfo, slice_number), offsetof(H264B2MbInfo, nnz_mask), offsetof(H264B2MbInfo, deblock_idc), offsetof(H264B2MbInfo, coef_mask));
+  printf("%zu %zu %zu\n", offsetof(H264B2MbMotion, ref_surf), offsetof(H264B2MbMotion, ref_ident), offsetof(H264B2MbMotion, wt_idx));
+  printf("%zu %zu %zu %zu\n", offsetof(H264B2PicParams, dst_surface), offsetof(H264B2PicParams, n_coefs), offsetof(H264B2PicParams, mb_info), offsetof(H264B2PicParams, level_scale8));
+  return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout.split("\n")
+    sizes = [int(x) for x in out[0].split()]
+    assert sizes == [abi.MB_INFO_DT.itemsize, abi.MB_MOTION_DT.itemsize, abi.WEIGHT_DT.itemsize, C.sizeof(abi.PicParams)]
+    f = abi.MB_INFO_DT.fields
+    assert [int(x) for x in out[1].split()] == [f["qpy"][1], f["slice_number"][1], f["nnz_mask"][1], f["deblock_idc"][1], f["coef_mask"][1]]
+    m = abi.MB_MOTION_DT.fields
+    assert [int(x) for x in out[2].split()] == [m["ref_surf"][1], m["ref_ident"][1], m["wt_idx"][1]]
+    P = abi.PicParams
+    assert [int(x) for x in out[3].split()] == [P.dst_surface.offset, P.n_coefs.offset, P.mb_info.offset, P.level_scale8.offset]
+
+
+def test_checksum_host_matches_numpy_definition():
+    lib = engine.load_library()
+    rng = np.random.default_rng(1)
+    for n in (0, 4, 4096, 120 * 68 * 384):
+        buf = rng.integers(0, 256, n).astype(np.uint8)
+        assert lib.h264b2_checksum_host(buf.ctypes.data, buf.size) == abi.checksum(buf.tobytes())
+
+
+def test_create_fails_loudly_without_gpu():
+    from conftest import _has_gpu
+    if _has_gpu():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(engine.EngineError, match="no CUDA device|no CPU fallback|failed"):
+        engine.Engine(0, 1, 8, 6)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "h264_video_decoder_demo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "oracle_py" not in txt and "liboracle" not in txt and "recon_oracle" not in txt, f"{fn} references the oracle"
