@@ -298,7 +298,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": {"inter": "k_inter", "intra": "k_intra", "deblock": "k_bs+k_deblock"}[dom], "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": round(dom_ms / ms, 3), "kernels": kernels}
-    launches = sum(kt[k]["launches"] for k in ("inter", "intra", "bs", "deblock"))
+    kernels["residual"] = {"ms_per_step": round(kt["residual"]["ms"] / args.steps, 3), "launches_per_step": kt["residual"]["launches"] // max(args.steps, 1)}
+    launches = sum(kt[k]["launches"] for k in ("residual", "inter", "intra", "bs", "deblock"))
 
     # ---- e2e: host buffers in, host pictures out, through the C ABI
     e2e = None

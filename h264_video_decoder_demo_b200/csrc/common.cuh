@@ -20,6 +20,7 @@ struct PicDev {
     uint8_t              *dst;         // Y plane of the destination surface; Cb = dst + W*H, Cr = Cb + W*H/4
     const uint8_t        *stream_base; // surface 0 of this picture's stream (reference surfaces = base + slot*frame_bytes)
     uint32_t             *bs;          // [n_mbs][64] packed boundary strengths (k_bs -> k_deblock)
+    int16_t              *res;         // [n_mbs][384] residual scratch (k_residual -> k_inter / k_intra)
     int                  *progress;    // [2][hmb] wavefront progress counters: [0] intra, [1] deblock
     unsigned long long    frame_bytes;
     int wmb, hmb, mbaff, cqp0, cqp1;

@@ -207,7 +207,10 @@ __device__ inline void deblock_mb(const PicDev &P, int a, int lane) {
     __syncwarp();
 }
 
+#include "deblock_fast.cuh"
+
 __global__ void __launch_bounds__(128) k_deblock(const PicDev *pics, int npics, int max_rows, int *ticket) {
+    __shared__ DbTile tiles[4];
     const int lane = threadIdx.x & 31;
     int t = 0;
     if (lane == 0) t = atomicAdd(ticket, 1);
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(128) k_deblock(const PicDev *pics, int npics, 
     const int rows = P.hmb / per, wmb = P.wmb, nmb = P.wmb * P.hmb;
     if (row >= rows) return;
     int *prog = P.progress + P.hmb;     // [1][row]
+    if (!P.mbaff && wmb <= 256) { deblock_row_fast(P, row, lane, tiles[threadIdx.x >> 5], prog); return; }
     const uint32_t *anyflag = P.bs + (size_t)nmb * 64;
     int seen = row == 0 ? wmb : 0;
     for (int xb = 0; xb < wmb; xb += 32) {

@@ -22,6 +22,7 @@
 #include "h264_recon_b200.h"
 #include "common.cuh"
 #include "residual.cuh"
+#include "residual_kernel.cuh"
 #include "inter.cuh"
 #include "intra.cuh"
 #include "deblock.cuh"
@@ -45,13 +46,14 @@ __global__ void k_checksum(const uint8_t *const *surf, size_t nwords, unsigned l
 }
 
 // ------------------------------------------------------------------ context
-enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 5 };
+enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 6 };
 
 struct H264B2Context {
     int device, n_streams, spp, wmb, hmb, nmb;
     size_t frame_bytes;
     uint8_t *surfaces;
     uint32_t *bs;
+    int16_t *res;
     int *progress;            // [n_streams][2][hmb] then DESC_RING*2 tickets
     size_t progress_ints;
     int16_t *ls_flat;         // ls4 [2][2][6][16] then ls8 [2][2][6][64]
@@ -146,6 +148,7 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaMalloc(&c->surfaces, total + (size_t)width_mbs * 64));
     CK(cudaMemset(c->surfaces, 0, total + (size_t)width_mbs * 64));
     CK(cudaMalloc(&c->bs, (size_t)n_streams * c->nmb * 65 * 4));
+    CK(cudaMalloc(&c->res, (size_t)n_streams * c->nmb * RES_MB_STRIDE * 2));
     c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 2;
     CK(cudaMalloc(&c->progress, c->progress_ints * 4));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
@@ -171,7 +174,7 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     if (!c) return fail(-1, "null context");
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc);
+    cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc);
     for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->compute_done[i]); }
     for (int i = 0; i < 2; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
     for (int i = 0; i < DESC_RING; i++) cudaEventDestroy(c->desc_ev[i]);
@@ -233,6 +236,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.stream_base = c->surfaces + (size_t)sids[i] * c->spp * c->frame_bytes;
         d.dst = (uint8_t *)d.stream_base + (size_t)p.dst_surface * c->frame_bytes;
         d.bs = c->bs + (size_t)sids[i] * c->nmb * 65;
+        d.res = c->res + (size_t)sids[i] * c->nmb * RES_MB_STRIDE;
         d.progress = c->progress + (size_t)sids[i] * 2 * c->hmb;
         d.frame_bytes = c->frame_bytes;
         d.wmb = c->wmb; d.hmb = c->hmb; d.mbaff = p.mbaff_frame_flag; d.cqp0 = p.chroma_qp_offset[0]; d.cqp1 = p.chroma_qp_offset[1];
@@ -247,9 +251,12 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
     CK(cudaMemsetAsync(c->progress, 0, c->progress_ints * 4, c->st));
     for (int i = 0; i < n; i++) if (pics[i].clear_surface) CK(cudaMemsetAsync(hd[i].dst, 0, c->frame_bytes, c->st));
     class_end(c, 0);
+    class_begin(c, 5);
+    k_residual<<<dim3((c->nmb + 7) / 8, n), 256, 0, c->st>>>(dd);
+    class_end(c, 5);
     if (any_inter) {
         class_begin(c, 1);
-        k_inter<<<dim3(c->nmb, n), 256, 0, c->st>>>(dd);
+        k_inter<<<dim3((c->nmb + 7) / 8, n), 128, 0, c->st>>>(dd);
         class_end(c, 1);
     }
     const int rows_total = n * c->hmb;

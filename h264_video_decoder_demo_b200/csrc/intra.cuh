@@ -9,12 +9,33 @@
 #pragma once
 #include "common.cuh"
 #include "residual.cuh"
+#include "residual_kernel.cuh"
 
 struct IntraWarpSmem {
     ResidualTile rt;
     int nb[36];
     int qa[28];
+    // fast (progressive) path: the macroblock and its neighbour samples staged in shared memory.
+    // Yt row 0 = samples of the row above (x = -1..23 at byte x+4), rows 1..16 = MB rows (byte 3 = left neighbour,
+    // bytes 4..19 = the MB's own samples).  Ct: same for Cb / Cr (x = -1..7 at byte x+4).
+    uint32_t Yt[17][8];
+    uint32_t Ct[2][9][4];
 };
+
+// sample of the current picture at MB-relative luma/chroma location (xN,yN) from the staged tile, or -1 when the
+// location is not available (6.4.12 for non-MBAFF frames, PB:2878; availability flags already include slice
+// membership and constrained_intra_pred)
+__device__ __forceinline__ int tile_sample(const IntraWarpSmem &S, int xN, int yN, int comp, int avA, int avB, int avC, int avD) {
+    const int n = comp ? 8 : 16;
+    if (yN < 0) {
+        const int ok = xN < 0 ? avD : xN < n ? avB : avC;
+        if (!ok) return -1;
+        return comp ? ((const uint8_t *)S.Ct[comp - 1][0])[xN + 4] : ((const uint8_t *)S.Yt[0])[xN + 4];
+    }
+    if (xN < 0) { if (!avA) return -1; return comp ? ((const uint8_t *)S.Ct[comp - 1][yN + 1])[3] : ((const uint8_t *)S.Yt[yN + 1])[3]; }
+    if (xN >= n) return -1;
+    return comp ? ((const uint8_t *)S.Ct[comp - 1][yN + 1])[xN + 4] : ((const uint8_t *)S.Yt[yN + 1])[xN + 4];
+}
 
 __device__ __forceinline__ int ld_acquire_flag(const int *p) {
     int v;
@@ -130,7 +151,10 @@ __device__ __forceinline__ void put_px(uint8_t *p, int have, int pred, int res) 
     *p = (uint8_t)clip255(pred + res);
 }
 
-// Reconstruct one intra (or I_PCM) macroblock with one warp.
+// Reconstruct one intra (or I_PCM) macroblock with one warp.  FAST (progressive pictures): neighbour samples and
+// the MB itself live in a shared-memory tile for the whole MB (one L2 round trip in, one out); otherwise every
+// sample access goes through the generic MBAFF-aware neighbour derivation.
+template <bool FAST>
 __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, int lane, IntraWarpSmem &S) {
     const int field = P.mbaff && (I.flags & H264B2_MBF_FIELD);
     const int ys = field ? 2 : 1;
@@ -149,13 +173,70 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
         }
         return;
     }
-    mb_residual(P, a, I, lane, 32, S.rt, SyncWarp());
+    int avA = 0, avB = 0, avC = 0, avD = 0;
+    if (FAST) {
+        // availability of the four neighbouring MBs (PB:2887-2947) incl. constrained_intra_pred (PB:1129)
+        const int w = P.wmb, mx = a % w;
+        const int nA = mx > 0 ? a - 1 : -1, nB = a - w, nC = (mx + 1 < w) ? a - w + 1 : -1, nD = mx > 0 ? a - w - 1 : -1;
+        avA = nA >= 0 && avail_addr(P, a, nA) && !(P.info[nA].flags & H264B2_MBF_CIP_UNAVAIL);
+        avB = nB >= 0 && avail_addr(P, a, nB) && !(P.info[nB].flags & H264B2_MBF_CIP_UNAVAIL);
+        avC = nC >= 0 && avail_addr(P, a, nC) && !(P.info[nC].flags & H264B2_MBF_CIP_UNAVAIL);
+        avD = nD >= 0 && avail_addr(P, a, nD) && !(P.info[nD].flags & H264B2_MBF_CIP_UNAVAIL);
+        // stage the tile: own samples (kept where a block is not predicted, Q15), the row above, the left column
+        const uint8_t *Yp = Y + (size_t)y0 * W + x0;
+#pragma unroll
+        for (int t = 0; t < 2; t++) { const int wd = lane + 32 * t, r = wd >> 2, j = wd & 3; S.Yt[1 + r][1 + j] = __ldcg((const uint32_t *)(Yp + (size_t)r * W + 4 * j)); }
+        { const int c = lane >> 4, cl = lane & 15, r = cl >> 1, j = cl & 1;
+          S.Ct[c][1 + r][1 + j] = __ldcg((const uint32_t *)((c ? Cr : Cb) + (size_t)(yc0 + r) * Wc + xc0 + 4 * j)); }
+        if (y0 > 0) {
+            if (lane < 7) { if ((lane > 0 || x0 > 0) && (lane < 5 || x0 + 16 < W)) S.Yt[0][lane] = __ldcg((const uint32_t *)(Yp - W - 4 + 4 * lane)); }
+            else if (lane >= 8 && lane < 14) { const int l = lane - 8, c = l / 3, j = l % 3;
+                if (j > 0 || x0 > 0) S.Ct[c][0][j] = __ldcg((const uint32_t *)((c ? Cr : Cb) + (size_t)(yc0 - 1) * Wc + xc0 - 4 + 4 * j)); }
+        }
+        if (x0 > 0) {
+            if (lane < 16) ((uint8_t *)S.Yt[1 + lane])[3] = __ldcg(Yp + (size_t)lane * W - 1);
+            else { const int l = lane - 16, c = l >> 3, r = l & 7; ((uint8_t *)S.Ct[c][1 + r])[3] = __ldcg((c ? Cr : Cb) + (size_t)(yc0 + r) * Wc + xc0 - 1); }
+        }
+    }
+    auto sample = [&](int xN, int yN, int comp) -> int {
+        if (FAST) return tile_sample(S, xN, yN, comp, avA, avB, avC, avD);
+        return nbr_sample(P, a, xN, yN, comp);
+    };
+    auto put = [&](int comp, int x, int y, int have, int pred, int r) {
+        if (FAST) {
+            uint8_t *px = comp ? &((uint8_t *)S.Ct[comp - 1][1 + y])[4 + x] : &((uint8_t *)S.Yt[1 + y])[4 + x];
+            if (!have) pred = *px;
+            *px = (uint8_t)clip255(pred + r);
+        } else {
+            uint8_t *px = comp == 0 ? &Y[(size_t)(y0 + y * ys) * W + x0 + x] : &(comp == 1 ? Cb : Cr)[(size_t)(yc0 + y * ys) * Wc + xc0 + x];
+            put_px(px, have, pred, r);
+        }
+    };
+    {   // stage this MB's residual (k_residual output) as a raster tile: luma 16x16, Cb 8x8, Cr 8x8
+        const int16_t *src = P.res + (size_t)a * RES_MB_STRIDE;
+        const int hasres = mb_has_residual(I);
+        const int t8eff = (I.flags & H264B2_MBF_T8x8) && cls != H264B2_MB_I16x16;
+        for (int e = lane; e < 384; e += 32) {
+            const int slot = e >> 4, inner = e & 15;
+            int v = 0, dsti;
+            if (slot < 16) {
+                if (hasres && luma_slot_coded(I.coef_mask, cls, t8eff, slot)) v = src[e];
+                dsti = ((slot >> 2) * 4 + (inner >> 2)) * 16 + (slot & 3) * 4 + (inner & 3);
+            } else {
+                const int c = (slot - 16) >> 2, b = (slot - 16) & 3;
+                if (hasres && chroma_blk_coded(I.coef_mask, c, b)) v = src[e];
+                dsti = 256 + c * 64 + ((b >> 1) * 4 + (inner >> 2)) * 8 + (b & 1) * 4 + (inner & 3);
+            }
+            S.rt.res[dsti] = (int16_t)v;
+        }
+        __syncwarp();
+    }
     const int16_t *res = S.rt.res;
 
     if (cls == H264B2_MB_I16x16) {                                      // PB:1847
         const int mode = I.pred16_chroma & 3;
-        if (lane < 16) S.nb[1 + lane] = nbr_sample(P, a, lane, -1, 0); else S.nb[17 + lane - 16] = nbr_sample(P, a, -1, lane - 16, 0);
-        if (lane == 0) S.nb[0] = nbr_sample(P, a, -1, -1, 0);
+        if (lane < 16) S.nb[1 + lane] = sample(lane, -1, 0); else S.nb[17 + lane - 16] = sample(-1, lane - 16, 0);
+        if (lane == 0) S.nb[0] = sample(-1, -1, 0);
         __syncwarp();
         const int *top = S.nb + 1, *left = S.nb + 17;
         const int corner = S.nb[0];
@@ -177,15 +258,15 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
         for (int i = lane; i < 256; i += 32) {
             const int x = i & 15, y = i >> 4;
             int pred = mode == 0 ? top[x] : mode == 1 ? left[y] : mode == 2 ? dcv : clip255((aa + bb * (x - 7) + cc * (y - 7) + 16) >> 5);
-            put_px(&Y[(size_t)(y0 + y * ys) * W + x0 + x], have, pred, res[y * 16 + x]);
+            put(0, x, y, have, pred, res[y * 16 + x]);
         }
     } else if (cls == H264B2_MB_I8x8) {                                 // PB:1423, PB:3651
         const uint64_t modes = P.modes[a];
         for (int b = 0; b < 4; b++) {
             const int mode = (int)((modes >> (4 * b)) & 15);
             const int xO = (b & 1) * 8, yO = (b >> 1) * 8;
-            if (lane < 9) S.nb[lane] = nbr_sample(P, a, xO - 1, yO + lane - 1, 0);
-            else if (lane < 25) S.nb[lane] = nbr_sample(P, a, xO + lane - 9, yO - 1, 0);
+            if (lane < 9) S.nb[lane] = sample(xO - 1, yO + lane - 1, 0);
+            else if (lane < 25) S.nb[lane] = sample(xO + lane - 9, yO - 1, 0);
             __syncwarp();
             {   // top-right substitution, then reference sample filtering 8.3.2.2.1 (PB:1536-1599); every lane computes one qa[]
                 int trmiss = 1;
@@ -220,7 +301,7 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
             for (int i = lane; i < 64; i += 32) {
                 const int x = i & 7, y = i >> 3;
                 int have; const int pred = pred8x8_px(mode, x, y, S.qa, have);
-                put_px(&Y[(size_t)(y0 + (yO + y) * ys) * W + x0 + xO + x], have, pred, res[(yO + y) * 16 + xO + x]);
+                put(0, xO + x, yO + y, have, pred, res[(yO + y) * 16 + xO + x]);
             }
             __syncwarp();
         }
@@ -229,15 +310,15 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
         for (int b = 0; b < 16; b++) {
             const int mode = (int)((modes >> (4 * b)) & 15);
             const int xO = blk_x(b), yO = blk_y(b);
-            if (lane < 5) S.nb[lane] = nbr_sample(P, a, xO - 1, yO + lane - 1, 0);
-            else if (lane < 13) { const int x = lane - 5; S.nb[lane] = (x > 3 && (b == 3 || b == 11)) ? -1 : nbr_sample(P, a, xO + x, yO - 1, 0); }
+            if (lane < 5) S.nb[lane] = sample(xO - 1, yO + lane - 1, 0);
+            else if (lane < 13) { const int x = lane - 5; S.nb[lane] = (x > 3 && (b == 3 || b == 11)) ? -1 : sample(xO + x, yO - 1, 0); }
             __syncwarp();
             if (lane == 0 && S.nb[9] < 0 && S.nb[10] < 0 && S.nb[11] < 0 && S.nb[12] < 0 && S.nb[8] >= 0) { S.nb[9] = S.nb[10] = S.nb[11] = S.nb[12] = S.nb[8]; }
             __syncwarp();
             if (lane < 16) {
                 const int x = lane & 3, y = lane >> 2;
                 int have; const int pred = pred4x4_px(mode, x, y, S.nb, have);
-                put_px(&Y[(size_t)(y0 + (yO + y) * ys) * W + x0 + xO + x], have, pred, res[(yO + y) * 16 + xO + x]);
+                put(0, xO + x, yO + y, have, pred, res[(yO + y) * 16 + xO + x]);
             }
             __syncwarp();
         }
@@ -247,13 +328,12 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     const int cmode = (I.pred16_chroma >> 2) & 3;
     for (int comp = 1; comp <= 2; comp++) {
         __syncwarp();
-        if (lane < 8) S.nb[1 + lane] = nbr_sample(P, a, lane, -1, comp);
-        else if (lane < 16) S.nb[9 + lane - 8] = nbr_sample(P, a, -1, lane - 8, comp);
-        else if (lane == 16) S.nb[0] = nbr_sample(P, a, -1, -1, comp);
+        if (lane < 8) S.nb[1 + lane] = sample(lane, -1, comp);
+        else if (lane < 16) S.nb[9 + lane - 8] = sample(-1, lane - 8, comp);
+        else if (lane == 16) S.nb[0] = sample(-1, -1, comp);
         __syncwarp();
         const int *top = S.nb + 1, *left = S.nb + 9;
         const int corner = S.nb[0];
-        uint8_t *pl = comp == 1 ? Cb : Cr;
         const int16_t *cres = res + 256 + (comp - 1) * 64;
         int topok = 1, leftok = 1;
         for (int i = 0; i < 8; i++) { if (top[i] < 0) topok = 0; if (left[i] < 0) leftok = 0; }
@@ -281,10 +361,17 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
             } else if (cmode == 1) pred = left[y];
             else if (cmode == 2) pred = top[x];
             else pred = clip255((aa + bb * (x - 3) + cc * (y - 3) + 16) >> 5);
-            put_px(&pl[(size_t)(yc0 + y * ys) * Wc + xc0 + x], have, pred, cres[y * 8 + x]);
+            put(comp, x, y, have, pred, cres[y * 8 + x]);
         }
     }
     __syncwarp();
+    if (FAST) {
+        uint8_t *Yp = Y + (size_t)y0 * W + x0;
+#pragma unroll
+        for (int t = 0; t < 2; t++) { const int wd = lane + 32 * t, r = wd >> 2, j = wd & 3; *(uint32_t *)(Yp + (size_t)r * W + 4 * j) = S.Yt[1 + r][1 + j]; }
+        const int c = lane >> 4, cl = lane & 15, r = cl >> 1, j = cl & 1;
+        *(uint32_t *)((c ? Cr : Cb) + (size_t)(yc0 + r) * Wc + xc0 + 4 * j) = S.Ct[c][1 + r][1 + j];
+    }
 }
 
 // Wavefront driver.  ticket: one counter per launch (zeroed by the host); tickets are handed out
@@ -324,7 +411,9 @@ __global__ void __launch_bounds__(128) k_intra(const PicDev *pics, int npics, in
             for (int s = 0; s < per; s++) {
                 const int a = (row * wmb + x) * per + s;
                 const H264B2MbInfo I = P.info[a];
-                if (I.mb_class >= H264B2_MB_I4x4 && I.mb_class <= H264B2_MB_IPCM) intra_mb(P, a, I, lane, sm[warp]);
+                if (I.mb_class >= H264B2_MB_I4x4 && I.mb_class <= H264B2_MB_IPCM) {
+                    if (P.mbaff) intra_mb<false>(P, a, I, lane, sm[warp]); else intra_mb<true>(P, a, I, lane, sm[warp]);
+                }
             }
             __threadfence();
             __syncwarp();

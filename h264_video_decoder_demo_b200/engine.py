@@ -43,7 +43,7 @@ _PROTOS = {
     "h264b2_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
 }
 ABI_SYMBOLS = sorted(_PROTOS)
-KERNEL_CLASSES = ("clear", "inter", "intra", "bs", "deblock")
+KERNEL_CLASSES = ("clear", "inter", "intra", "bs", "deblock", "residual")
 
 
 class EngineError(RuntimeError):
@@ -185,8 +185,8 @@ class Engine:
         return ms.value
 
     def kernel_times(self) -> Dict[str, Dict[str, float]]:
-        ms = (C.c_float * 5)()
-        n = (C.c_int64 * 5)()
+        ms = (C.c_float * 6)()
+        n = (C.c_int64 * 6)()
         self._ck(self.lib.h264b2_kernel_times(self._ctx, ms, n))
         return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(KERNEL_CLASSES)}
 

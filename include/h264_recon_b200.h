@@ -193,9 +193,9 @@ int h264b2_sync(H264B2Context *ctx);
 /* Event timing on the context's launch stream (CUDA events; for bench.py). */
 int h264b2_timer_start(H264B2Context *ctx);
 int h264b2_timer_stop(H264B2Context *ctx, float *elapsed_ms);
-/* Per-kernel-class accumulated device time (ms) and launch counts of the last timed region:
- * [0] clears/memsets, [1] k_inter (MC + inter residual), [2] k_intra, [3] k_bs, [4] k_deblock. */
-int h264b2_kernel_times(H264B2Context *ctx, float *ms5, int64_t *launches);
+/* Per-kernel-class accumulated device time (ms) and launch counts of the last timed region, 6 entries each:
+ * [0] clears/memsets, [1] k_inter (MC + residual add), [2] k_intra, [3] k_bs, [4] k_deblock, [5] k_residual. */
+int h264b2_kernel_times(H264B2Context *ctx, float *ms6, int64_t *launches6);
 
 /* ABI version / last error string (static storage). */
 int h264b2_abi_version(void);

@@ -38,7 +38,11 @@ class OracleDPB:
 
     def __init__(self, width_mbs, height_mbs, n_surfaces=17):
         self.frame_bytes = width_mbs * height_mbs * 384
-        self.surfaces = [np.zeros(self.frame_bytes, dtype=np.uint8) for _ in range(n_surfaces)]
+        # one contiguous allocation + zero tail padding, exactly like the engine's DPB: a bottom-field view
+        # clamps x to 2W-1 (Q4) and can read up to one chroma row past the end of a surface, i.e. into the
+        # next surface (undefined behaviour in the reference; defined as "what follows in the DPB" here)
+        self._store = np.zeros(n_surfaces * self.frame_bytes + width_mbs * 64, dtype=np.uint8)
+        self.surfaces = [self._store[i * self.frame_bytes:(i + 1) * self.frame_bytes] for i in range(n_surfaces)]
         self._ptrs = (C.c_void_p * n_surfaces)(*[s.ctypes.data for s in self.surfaces])
         self.n = n_surfaces
 

@@ -74,6 +74,38 @@ def test_all_streams_in_one_batch_and_host_submit():
     eng.close()
 
 
+def _describe(got, ref, pic, wmb, hmb):
+    W, H = wmb * 16, hmb * 16
+    d = np.nonzero(got != ref)[0]
+    names = {0: "NA", 1: "I4x4", 2: "I8x8", 3: "I16x16", 4: "IPCM", 5: "INTER"}
+    out = [f"{d.size} bytes differ"]
+    seen = set()
+    for off in d:
+        off = int(off)
+        if off < W * H:
+            comp, x, y, mbs, w = "Y", off % W, off // W, 16, W
+        else:
+            o2 = off - W * H
+            comp = "Cb" if o2 < W * H // 4 else "Cr"
+            o2 %= W * H // 4
+            x, y, mbs, w = o2 % (W // 2), o2 // (W // 2), 8, W // 2
+        mbx, mby = x // mbs, y // mbs
+        if pic.mbaff:
+            pr = (mby // 2) * wmb + mbx
+            addrs = [2 * pr, 2 * pr + 1]
+        else:
+            addrs = [mby * wmb + mbx]
+        key = (comp, tuple(addrs))
+        if key in seen:
+            continue
+        seen.add(key)
+        info = "; ".join(f"a={a} {names[int(pic.mb_info['mb_class'][a])]} flags={int(pic.mb_info['flags'][a]):#x} slice={int(pic.mb_info['slice_number'][a])} cm={int(pic.mb_info['coef_mask'][a]):#x}" for a in addrs)
+        out.append(f"{comp}({x},{y}) gpu={got[off]} oracle={ref[off]} MB({mbx},{mby}) [{info}]")
+        if len(seen) >= 6:
+            break
+    return " | ".join(out)
+
+
 def _oracle_vs_gpu(rng, wmb, hmb, pics_kwargs, smooth):
     import oracle_py as O
     import synth
@@ -98,8 +130,7 @@ def _oracle_vs_gpu(rng, wmb, hmb, pics_kwargs, smooth):
             eng.submit([0], [p])
             got = eng.read_picture(0, 0)
             if not np.array_equal(got, dpb.surfaces[0]):
-                d = np.nonzero(got != dpb.surfaces[0])[0]
-                raise AssertionError(f"{kw} deblock={dbk}: {d.size} bytes differ, first at {d[0]} (gpu {got[d[0]]} oracle {dpb.surfaces[0][d[0]]})")
+                raise AssertionError(f"{kw} deblock={dbk}: " + _describe(got, dpb.surfaces[0], pic, wmb, hmb))
     eng.close()
 
 
