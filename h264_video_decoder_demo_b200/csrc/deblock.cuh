@@ -109,6 +109,34 @@ __global__ void __launch_bounds__(256) k_bs(const PicDev *pics) {
     if (a >= nmb || !P.deblock_enable || a >= P.deblock_stop) return;
     const H264B2MbInfo I = P.info[a];
     const DbCtx c = db_ctx(P, a, I);
+    if (!P.mbaff) {
+        // ---- compact record for progressive pictures (consumed by deblock_row_fast): without MBAFF the strength
+        // is constant over each 4-sample segment and chroma line k reuses luma line 2k (DB:871-880), so 16 vertical
+        // + 16 horizontal values describe the MB.  16 words per MB at bs[a*16]:
+        //   [0..1] vertical nibbles (index edge*4 + segment), [2..3] horizontal nibbles,
+        //   [4 + comp*3 + t] thresholds alpha | beta<<8 | indexA<<16 for t = 0 left edge, 1 top edge, 2 internal edges
+        const int dir = lane >> 4, edge = (lane >> 2) & 3, seg = lane & 3;
+        const int on = edge == 0 ? (dir ? c.top : c.left) : (c.internal && (!c.t8 || edge == 2));
+        const int bS = on ? edge_bs(P, a, 0, dir ? c.B : c.A, !dir, 0, 4 * edge, 4 * seg) : 0;
+        const int idx = lane & 15;
+        const uint32_t val = (uint32_t)bS << (4 * (idx & 7));
+        const int word = dir * 2 + (idx >> 3);
+        uint32_t r0 = __reduce_or_sync(0xffffffffu, word == 0 ? val : 0u), r1 = __reduce_or_sync(0xffffffffu, word == 1 ? val : 0u);
+        uint32_t r2 = __reduce_or_sync(0xffffffffu, word == 2 ? val : 0u), r3 = __reduce_or_sync(0xffffffffu, word == 3 ? val : 0u);
+        uint32_t *rec = P.bs + (size_t)a * 16;
+        if (lane == 0) { *(uint4 *)rec = make_uint4(r0, r1, r2, r3); P.bs[(size_t)nmb * 64 + a] = (r0 | r1 | r2 | r3) != 0; }
+        if (lane < 9) {
+            const int cc = lane / 3, t = lane % 3;
+            int qq = I.mb_class == H264B2_MB_IPCM ? 0 : I.qpy, qp = qq;
+            const int n = t == 0 ? c.A : t == 1 ? c.B : -1;
+            if (n >= 0) { const H264B2MbInfo In = P.info[n]; qp = In.mb_class == H264B2_MB_IPCM ? 0 : In.qpy; }
+            if (cc) { qq = chroma_qp(P, qq, cc - 1); qp = chroma_qp(P, qp, cc - 1); }
+            const int qpav = (qp + qq + 1) >> 1;
+            const int ia = clip3i(0, 51, qpav + I.filter_offset_a), ib = clip3i(0, 51, qpav + I.filter_offset_b);
+            rec[4 + lane] = (uint32_t)g_alpha_tab[ia] | ((uint32_t)g_beta_tab[ib] << 8) | ((uint32_t)ia << 16);
+        }
+        return;
+    }
     const int comp = lane < 16 ? 0 : lane < 24 ? 1 : 2;
     const int k = comp ? (lane & 7) : lane;
     const int ne = comp ? 2 : 4;
@@ -209,23 +237,25 @@ __device__ inline void deblock_mb(const PicDev &P, int a, int lane) {
 
 #include "deblock_fast.cuh"
 
-__global__ void __launch_bounds__(128) k_deblock(const PicDev *pics, int npics, int max_rows, int *ticket) {
-    __shared__ DbTile tiles[4];
-    const int lane = threadIdx.x & 31;
-    int t = 0;
-    if (lane == 0) t = atomicAdd(ticket, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= npics * max_rows) return;
+__global__ void __launch_bounds__(WF_THREADS, 2) k_deblock(const PicDev *pics, int npics, int bands, int *ticket) {
+    __shared__ DbTile tiles[WF_ROWS];
+    __shared__ int s_prog[WF_ROWS];
+    __shared__ int s_ticket;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
+    if (threadIdx.x < WF_ROWS) s_prog[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = s_ticket;
+    if (t >= npics * bands) return;
     const PicDev &P = pics[t % npics];
     if (!P.deblock_enable) return;
-    const int row = t / npics;
+    const int row = (t / npics) * WF_ROWS + warp;
     const int per = P.mbaff ? 2 : 1;
     const int rows = P.hmb / per, wmb = P.wmb, nmb = P.wmb * P.hmb;
     if (row >= rows) return;
-    int *prog = P.progress + P.hmb;     // [1][row]
-    if (!P.mbaff && wmb <= 256) { deblock_row_fast(P, row, lane, tiles[threadIdx.x >> 5], prog); return; }
+    RowSync rs = rs_init(s_prog, warp, row, rows, P.progress + P.hmb, wmb);     // progress[1][row]
+    if (!P.mbaff && wmb <= 256) { deblock_row_fast(P, row, lane, tiles[warp], rs); return; }
     const uint32_t *anyflag = P.bs + (size_t)nmb * 64;
-    int seen = row == 0 ? wmb : 0;
     for (int xb = 0; xb < wmb; xb += 32) {
         const int xl = xb + lane;
         int work = 0;
@@ -234,24 +264,13 @@ __global__ void __launch_bounds__(128) k_deblock(const PicDev *pics, int npics, 
         while (mask) {
             const int x = xb + __ffs(mask) - 1;
             mask &= mask - 1;
-            const int need = min(x + 2, wmb);
-            if (seen < need) {
-                if (lane == 0) {
-                    st_relaxed_flag(&prog[row], x);
-                    while ((seen = ld_acquire_flag(&prog[row - 1])) < need) __nanosleep(20);
-                }
-                seen = __shfl_sync(0xffffffffu, seen, 0);
-                __threadfence();
-            }
+            rs_wait(rs, min(x + 2, wmb), x, lane);
             for (int s = 0; s < per; s++) {
                 const int a = (row * wmb + x) * per + s;
                 if (a < P.deblock_stop && anyflag[a]) deblock_mb(P, a, lane);
             }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_relaxed_flag(&prog[row], x + 1);
+            rs_publish(rs, x + 1, lane);
         }
     }
-    __syncwarp();
-    if (lane == 0) st_relaxed_flag(&prog[row], wmb);
+    rs_publish(rs, wmb, lane);
 }

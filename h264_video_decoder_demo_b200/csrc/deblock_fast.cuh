@@ -12,10 +12,11 @@
 //   * progress is published with st.release after the MB's rows are written back.
 #pragma once
 #include "common.cuh"
+#include "wavefront.cuh"
 
 struct DbTile {
     uint32_t L[20][5];        // luma rows -4..15 (index r+4); word 0 = columns -4..-1, words 1..4 = columns 0..15
-    uint32_t C[2][10][3];     // Cb, Cr rows -2..7 (index r+2); word 0 = columns -4..-1, words 1..2 = columns 0..7
+    uint32_t C[2][12][3];     // Cb, Cr rows -4..7 (index r+4; rows -4,-3 unused); word 0 = columns -4..-1, words 1..2 = columns 0..7
     uint32_t work[8];         // bit x: macroblock x of this row has at least one non-zero boundary strength
 };
 
@@ -24,13 +25,8 @@ __device__ __forceinline__ void st_release_flag(int *p, int v) {
 }
 
 struct DbThr { int alpha, beta, ia; };
-__device__ __forceinline__ DbThr db_thr(int qpp, int qpq, int offa, int offb) {   // DB:1314
-    const int qpav = (qpp + qpq + 1) >> 1;
-    DbThr t;
-    t.ia = clip3i(0, 51, qpav + offa);
-    const int ib = clip3i(0, 51, qpav + offb);
-    t.alpha = g_alpha_tab[t.ia]; t.beta = g_beta_tab[ib];
-    return t;
+__device__ __forceinline__ DbThr db_thr_unpack(uint32_t w) {      // packed by k_bs (DB:1314)
+    DbThr t; t.alpha = w & 0xff; t.beta = (w >> 8) & 0xff; t.ia = (w >> 16) & 0xff; return t;
 }
 
 // one sample line: Pw = p3 p2 p1 p0 (byte 3 = p0), Qw = q0 q1 q2 q3 (byte 0 = q0).  DB:1373 / DB:1481.
@@ -67,7 +63,7 @@ __device__ __forceinline__ int db_next_work(const uint32_t *work, int x, int wmb
     return wmb;
 }
 
-struct DbPrefetch { uint32_t y0, y1, c, l; };   // own luma words (lane, lane+32), own chroma word, left-column word
+struct DbPrefetch { uint32_t y0, y1, c, l; uint4 bs; uint32_t tA, tB, tI; };   // own luma words (lane, lane+32), own chroma word, left-column word, k_bs record
 
 // lanes: luma word w = lane + 32 t -> row w/4, word w%4; chroma: lanes 0-15 Cb word (row = l/2, word l%2), 16-31 Cr
 __device__ __forceinline__ DbPrefetch db_prefetch(const PicDev &P, int row, int x, int lane, int need_left) {
@@ -79,6 +75,10 @@ __device__ __forceinline__ DbPrefetch db_prefetch(const PicDev &P, int row, int 
     f.y1 = __ldcg((const uint32_t *)(Y + (size_t)(8 + (lane >> 2)) * W + (lane & 3) * 4));
     const int cl = lane & 15;
     f.c = __ldcg((const uint32_t *)(C + (size_t)(cl >> 1) * Wc + (cl & 1) * 4));
+    {   const int comp = lane < 16 ? 0 : lane < 24 ? 1 : 2;
+        const uint32_t *rec = P.bs + (size_t)(row * P.wmb + x) * 16;
+        f.bs = *(const uint4 *)rec;
+        f.tA = rec[4 + comp * 3]; f.tB = rec[5 + comp * 3]; f.tI = rec[6 + comp * 3]; }
     f.l = 0;
     if (need_left && x > 0) {
         if (lane < 16) f.l = __ldcg((const uint32_t *)(Y + (size_t)lane * W - 4));
@@ -89,7 +89,7 @@ __device__ __forceinline__ DbPrefetch db_prefetch(const PicDev &P, int row, int 
 }
 
 // Deblock one MB row of a progressive picture.  prog = this picture's deblock progress counters.
-__device__ inline void deblock_row_fast(const PicDev &P, int row, int lane, DbTile &T, int *prog) {
+__device__ inline void deblock_row_fast(const PicDev &P, int row, int lane, DbTile &T, RowSync &rs) {
     const int wmb = P.wmb, nmb = P.wmb * P.hmb;
     const int W = wmb * 16, H = P.hmb * 16, Wc = W >> 1;
     const uint32_t *anyflag = P.bs + (size_t)nmb * 64;
@@ -103,90 +103,80 @@ __device__ inline void deblock_row_fast(const PicDev &P, int row, int lane, DbTi
     __syncwarp();
     const int comp = lane < 16 ? 0 : lane < 24 ? 1 : 2;
     const int k = comp ? (lane & 7) : lane;
-    int seen = row == 0 ? wmb : 0;
     int x = db_next_work(T.work, -1, wmb);
     int carry_x = -2;                                    // tile word 0 holds the right columns of MB carry_x
     DbPrefetch pf;
     if (x < wmb) pf = db_prefetch(P, row, x, lane, 1);
     while (x < wmb) {
-        const int a = row * wmb + x;
         // ---- stage the prefetched MB into the tile
         T.L[4 + (lane >> 2)][1 + (lane & 3)] = pf.y0;
         T.L[12 + (lane >> 2)][1 + (lane & 3)] = pf.y1;
-        { const int cl = lane & 15; T.C[lane >> 4][2 + (cl >> 1)][1 + (cl & 1)] = pf.c; }
-        if (carry_x != x - 1 && x > 0) { if (lane < 16) T.L[4 + lane][0] = pf.l; else T.C[(lane - 16) >> 3][2 + ((lane - 16) & 7)][0] = pf.l; }
+        { const int cl = lane & 15; T.C[lane >> 4][4 + (cl >> 1)][1 + (cl & 1)] = pf.c; }
+        if (carry_x != x - 1 && x > 0) { if (lane < 16) T.L[4 + lane][0] = pf.l; else T.C[(lane - 16) >> 3][4 + ((lane - 16) & 7)][0] = pf.l; }
+        // ---- per-MB parameters (prefetched k_bs record): this lane's strengths, one nibble per filter step.
+        //      Luma and chroma lanes run the SAME 4-step sequence (chroma has strengths only in steps 0 and 1,
+        //      which are its edges 0 and 4 = luma edges 0 and 8), so the warp never serialises the two planes.
+        uint32_t v, h;
+        {
+            const unsigned long long bv = (unsigned long long)pf.bs.x | ((unsigned long long)pf.bs.y << 32);
+            const unsigned long long bh = (unsigned long long)pf.bs.z | ((unsigned long long)pf.bs.w << 32);
+            const int seg = comp ? k >> 1 : k >> 2;      // chroma line k <-> luma line 2k
+            const int e1 = comp ? 8 : 4;                 // nibble index of the step-1 edge: luma edge 4, chroma edge 4 (= luma edge 8)
+            v = (uint32_t)((bv >> (4 * seg)) & 15) | ((uint32_t)((bv >> (4 * (e1 + seg))) & 15) << 4);
+            h = (uint32_t)((bh >> (4 * seg)) & 15) | ((uint32_t)((bh >> (4 * (e1 + seg))) & 15) << 4);
+            if (!comp) {
+                v |= ((uint32_t)((bv >> (4 * (8 + seg))) & 15) << 8) | ((uint32_t)((bv >> (4 * (12 + seg))) & 15) << 12);
+                h |= ((uint32_t)((bh >> (4 * (8 + seg))) & 15) << 8) | ((uint32_t)((bh >> (4 * (12 + seg))) & 15) << 12);
+            }
+        }
+        const DbThr tA = db_thr_unpack(pf.tA), tB = db_thr_unpack(pf.tB), tI = db_thr_unpack(pf.tI);
         const int xn = db_next_work(T.work, x, wmb);
         if (xn < wmb) pf = db_prefetch(P, row, xn, lane, xn != x + 1);
-        // ---- per-MB parameters
-        const uint32_t v = P.bs[(size_t)a * 64 + lane], h = P.bs[(size_t)a * 64 + 32 + lane];
-        const H264B2MbInfo I = P.info[a];
-        int xW, yW;
-        const int A = nbr_nonmbaff(P, a, -1, 0, 16, 16, xW, yW), B = nbr_nonmbaff(P, a, 0, -1, 16, 16, xW, yW);
-        int qq = I.mb_class == H264B2_MB_IPCM ? 0 : I.qpy;
-        int qa = qq, qb = qq;
-        if (A >= 0) { const H264B2MbInfo IA = P.info[A]; qa = IA.mb_class == H264B2_MB_IPCM ? 0 : IA.qpy; }
-        if (B >= 0) { const H264B2MbInfo IB = P.info[B]; qb = IB.mb_class == H264B2_MB_IPCM ? 0 : IB.qpy; }
-        if (comp) { qq = chroma_qp(P, qq, comp - 1); qa = chroma_qp(P, qa, comp - 1); qb = chroma_qp(P, qb, comp - 1); }
-        const DbThr tI = db_thr(qq, qq, I.filter_offset_a, I.filter_offset_b);
-        const DbThr tA = db_thr(qa, qq, I.filter_offset_a, I.filter_offset_b);
-        const DbThr tB = db_thr(qb, qq, I.filter_offset_a, I.filter_offset_b);
         const int topf = __any_sync(0xffffffffu, (h & 15u) != 0);
-        // ---- rows of the MB above (after the row-above flag)
-        if (topf) {
-            const int need = min(x + 2, wmb);
-            if (seen < need) {
-                if (lane == 0) {
-                    st_release_flag(&prog[row], x);
-                    while ((seen = ld_acquire_flag(&prog[row - 1])) < need) __nanosleep(20);
-                }
-                seen = __shfl_sync(0xffffffffu, seen, 0);
-                __syncwarp();
-            }
-            if (lane < 16) T.L[lane >> 2][1 + (lane & 3)] = __ldcg((const uint32_t *)(P.dst + (size_t)(row * 16 - 4 + (lane >> 2)) * W + x * 16 + (lane & 3) * 4));
-            else if (lane < 24) { const int l = lane - 16, c = l >> 2, r = (l >> 1) & 1, w = l & 1;
-                T.C[c][r][1 + w] = __ldcg((const uint32_t *)(P.dst + (size_t)W * H + (c ? (size_t)Wc * (H >> 1) : 0) + (size_t)(row * 8 - 2 + r) * Wc + x * 8 + w * 4)); }
-        }
+        // ---- rows of the MB above: only the horizontal phase needs them.  If the row above is already far enough,
+        //      fetch them now so that the L2 latency hides behind the vertical phase; otherwise wait after it.
+        const uint8_t *toprow = nullptr;
+        if (lane < 16) toprow = P.dst + (size_t)(row * 16 - 4 + (lane >> 2)) * W + x * 16 + (lane & 3) * 4;
+        else if (lane < 24) { const int l = lane - 16; toprow = P.dst + (size_t)W * H + ((l >> 2) ? (size_t)Wc * (H >> 1) : 0) + (size_t)(row * 8 - 2 + ((l >> 1) & 1)) * Wc + x * 8 + (l & 1) * 4; }
+        uint32_t topw = 0;
+        const bool early = topf && rs_try(rs, min(x + 2, wmb), lane);
+        if (early && toprow) topw = __ldcg((const uint32_t *)toprow);
         __syncwarp();
-        // ---- vertical edges: lane = sample row; edge i lies between tile words i and i+1
+        uint32_t *rowp = comp ? &T.C[comp - 1][4 + k][0] : &T.L[4 + k][0];
+        // ---- vertical edges: lane = sample row; step i filters the edge between tile words i and i+1
         if (v) {
-            if (!comp) {
-                uint32_t w0 = T.L[4 + k][0], w1 = T.L[4 + k][1], w2 = T.L[4 + k][2], w3 = T.L[4 + k][3], w4 = T.L[4 + k][4];
-                if (v & 0xF) filter_words(w0, w1, v & 15, tA, 0);
-                if (v & 0xF0) filter_words(w1, w2, (v >> 4) & 15, tI, 0);
-                if (v & 0xF00) filter_words(w2, w3, (v >> 8) & 15, tI, 0);
-                if (v & 0xF000) filter_words(w3, w4, (v >> 12) & 15, tI, 0);
-                T.L[4 + k][0] = w0; T.L[4 + k][1] = w1; T.L[4 + k][2] = w2; T.L[4 + k][3] = w3; T.L[4 + k][4] = w4;
-            } else {
-                uint32_t w0 = T.C[comp - 1][2 + k][0], w1 = T.C[comp - 1][2 + k][1], w2 = T.C[comp - 1][2 + k][2];
-                if (v & 0xF) filter_words(w0, w1, v & 15, tA, 1);
-                if (v & 0xF0) filter_words(w1, w2, (v >> 4) & 15, tI, 1);
-                T.C[comp - 1][2 + k][0] = w0; T.C[comp - 1][2 + k][1] = w1; T.C[comp - 1][2 + k][2] = w2;
-            }
+            uint32_t w0 = rowp[0], w1 = rowp[1], w2 = rowp[2], w3 = 0, w4 = 0;
+            if (!comp) { w3 = rowp[3]; w4 = rowp[4]; }
+            if (v & 0xF) filter_words(w0, w1, v & 15, tA, comp);
+            if (v & 0xF0) filter_words(w1, w2, (v >> 4) & 15, tI, comp);
+            if (v & 0xF00) filter_words(w2, w3, (v >> 8) & 15, tI, comp);
+            if (v & 0xF000) filter_words(w3, w4, (v >> 12) & 15, tI, comp);
+            rowp[0] = w0; rowp[1] = w1; rowp[2] = w2;
+            if (!comp) { rowp[3] = w3; rowp[4] = w4; }
+        }
+        if (topf) {
+            if (!early) { rs_wait(rs, min(x + 2, wmb), x, lane); if (toprow) topw = __ldcg((const uint32_t *)toprow); }
+            if (lane < 16) T.L[lane >> 2][1 + (lane & 3)] = topw;
+            else if (lane < 24) { const int l = lane - 16; T.C[l >> 2][2 + ((l >> 1) & 1)][1 + (l & 1)] = topw; }
         }
         __syncwarp();
-        // ---- horizontal edges: lane = sample column; gather the column into words (4 rows each)
+        // ---- horizontal edges: lane = sample column; gather the column into words of 4 rows, same 4 steps
         if (h) {
-            if (!comp) {
-                uint8_t *col = (uint8_t *)&T.L[0][0] + 4 + k;
-                uint32_t cw[5];
+            uint8_t *col = comp ? (uint8_t *)&T.C[comp - 1][0][0] + 4 + k : (uint8_t *)&T.L[0][0] + 4 + k;
+            const int sb = comp ? 12 : 20;
+            uint32_t cw[5];
 #pragma unroll
-                for (int j = 0; j < 5; j++) cw[j] = (uint32_t)col[(4 * j) * 20] | ((uint32_t)col[(4 * j + 1) * 20] << 8) | ((uint32_t)col[(4 * j + 2) * 20] << 16) | ((uint32_t)col[(4 * j + 3) * 20] << 24);
-                if (h & 0xF) filter_words(cw[0], cw[1], h & 15, tB, 0);
-                if (h & 0xF00) filter_words(cw[1], cw[2], (h >> 8) & 15, tI, 0);
-                if (h & 0xF000) filter_words(cw[2], cw[3], (h >> 12) & 15, tI, 0);
-                if (h & 0xF0000) filter_words(cw[3], cw[4], (h >> 16) & 15, tI, 0);
+            for (int j = 0; j < 5; j++) {
+                if (j < 3 || !comp) cw[j] = (uint32_t)col[(4 * j) * sb] | ((uint32_t)col[(4 * j + 1) * sb] << 8) | ((uint32_t)col[(4 * j + 2) * sb] << 16) | ((uint32_t)col[(4 * j + 3) * sb] << 24);
+                else cw[j] = 0;
+            }
+            if (h & 0xF) filter_words(cw[0], cw[1], h & 15, tB, comp);
+            if (h & 0xF0) filter_words(cw[1], cw[2], (h >> 4) & 15, tI, comp);
+            if (h & 0xF00) filter_words(cw[2], cw[3], (h >> 8) & 15, tI, comp);
+            if (h & 0xF000) filter_words(cw[3], cw[4], (h >> 12) & 15, tI, comp);
 #pragma unroll
-                for (int j = 0; j < 5; j++) { col[(4 * j) * 20] = (uint8_t)cw[j]; col[(4 * j + 1) * 20] = (uint8_t)(cw[j] >> 8); col[(4 * j + 2) * 20] = (uint8_t)(cw[j] >> 16); col[(4 * j + 3) * 20] = (uint8_t)(cw[j] >> 24); }
-            } else {
-                uint8_t *col = (uint8_t *)&T.C[comp - 1][0][0] + 4 + k;
-                uint32_t c0 = ((uint32_t)col[0] << 16) | ((uint32_t)col[12] << 24);      // rows -2, -1 = p1, p0
-                uint32_t c1 = (uint32_t)col[2 * 12] | ((uint32_t)col[3 * 12] << 8) | ((uint32_t)col[4 * 12] << 16) | ((uint32_t)col[5 * 12] << 24);
-                uint32_t c2 = (uint32_t)col[6 * 12] | ((uint32_t)col[7 * 12] << 8) | ((uint32_t)col[8 * 12] << 16) | ((uint32_t)col[9 * 12] << 24);
-                if (h & 0xF) filter_words(c0, c1, h & 15, tB, 1);
-                if (h & 0xF00) filter_words(c1, c2, (h >> 8) & 15, tI, 1);
-                col[12] = (uint8_t)(c0 >> 24);
-                col[2 * 12] = (uint8_t)c1; col[5 * 12] = (uint8_t)(c1 >> 24);
-                col[6 * 12] = (uint8_t)c2;
+            for (int j = 0; j < 5; j++) {
+                if (j < 3 || !comp) { col[(4 * j) * sb] = (uint8_t)cw[j]; col[(4 * j + 1) * sb] = (uint8_t)(cw[j] >> 8); col[(4 * j + 2) * sb] = (uint8_t)(cw[j] >> 16); col[(4 * j + 3) * sb] = (uint8_t)(cw[j] >> 24); }
             }
         }
         __syncwarp();
@@ -201,26 +191,24 @@ __device__ inline void deblock_row_fast(const PicDev &P, int row, int lane, DbTi
             }
             const int c = lane >> 4, cl = lane & 15, r = cl >> 1, j = cl & 1;
             uint8_t *Cp = P.dst + (size_t)W * H + (c ? (size_t)Wc * (H >> 1) : 0) + (size_t)(row * 8) * Wc + x * 8;
-            if (j > 0 || x > 0) *(uint32_t *)(Cp + (size_t)r * Wc + j * 4 - 4) = T.C[c][2 + r][j];
+            if (j > 0 || x > 0) *(uint32_t *)(Cp + (size_t)r * Wc + j * 4 - 4) = T.C[c][4 + r][j];
             if (xn != x + 1 || xn >= wmb) {      // nobody will carry our right-hand columns: write them now
                 if (lane < 16) *(uint32_t *)(Y + (size_t)lane * W + 12) = T.L[4 + lane][4];
                 else { const int l = lane - 16, cc = l >> 3, rr = l & 7;
-                    *(uint32_t *)(P.dst + (size_t)W * H + (cc ? (size_t)Wc * (H >> 1) : 0) + (size_t)(row * 8 + rr) * Wc + x * 8 + 4) = T.C[cc][2 + rr][2]; }
+                    *(uint32_t *)(P.dst + (size_t)W * H + (cc ? (size_t)Wc * (H >> 1) : 0) + (size_t)(row * 8 + rr) * Wc + x * 8 + 4) = T.C[cc][4 + rr][2]; }
             }
             if (topf) {
                 if (lane < 12) { const int rr = 1 + lane / 4, jj = lane & 3; *(uint32_t *)(Y + (size_t)(rr - 4) * W + jj * 4) = T.L[rr][1 + jj]; }
                 else if (lane >= 16 && lane < 20) { const int l = lane - 16, cc = l >> 1, jj = l & 1;
-                    *(uint32_t *)(P.dst + (size_t)W * H + (cc ? (size_t)Wc * (H >> 1) : 0) + (size_t)(row * 8 - 1) * Wc + x * 8 + jj * 4) = T.C[cc][1][1 + jj]; }
+                    *(uint32_t *)(P.dst + (size_t)W * H + (cc ? (size_t)Wc * (H >> 1) : 0) + (size_t)(row * 8 - 1) * Wc + x * 8 + jj * 4) = T.C[cc][3][1 + jj]; }
             }
         }
         // ---- carry the right-hand columns to the next MB
         if (lane < 16) T.L[4 + lane][0] = T.L[4 + lane][4];
-        else { const int l = lane - 16; T.C[l >> 3][2 + (l & 7)][0] = T.C[l >> 3][2 + (l & 7)][2]; }
+        else { const int l = lane - 16; T.C[l >> 3][4 + (l & 7)][0] = T.C[l >> 3][4 + (l & 7)][2]; }
         carry_x = x;
-        __syncwarp();
-        if (lane == 0) st_release_flag(&prog[row], x + 1);
+        rs_publish(rs, x + 1, lane);
         x = xn;
     }
-    __syncwarp();
-    if (lane == 0) st_release_flag(&prog[row], wmb);
+    rs_publish(rs, wmb, lane);
 }

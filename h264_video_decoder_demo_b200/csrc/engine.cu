@@ -259,16 +259,16 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         k_inter<<<dim3((c->nmb + 7) / 8, n), 128, 0, c->st>>>(dd);
         class_end(c, 1);
     }
-    const int rows_total = n * c->hmb;
+    const int bands = (c->hmb + WF_ROWS - 1) / WF_ROWS;
     class_begin(c, 2);
-    k_intra<<<(rows_total + 3) / 4, 128, 0, c->st>>>(dd, n, c->hmb, tickets);
+    k_intra<<<n * bands, WF_THREADS, 0, c->st>>>(dd, n, bands, tickets);
     class_end(c, 2);
     if (any_deblock) {
         class_begin(c, 3);
         k_bs<<<dim3((c->nmb + 7) / 8, n), 256, 0, c->st>>>(dd);
         class_end(c, 3);
         class_begin(c, 4);
-        k_deblock<<<(rows_total + 3) / 4, 128, 0, c->st>>>(dd, n, c->hmb, tickets + 1);
+        k_deblock<<<n * bands, WF_THREADS, 0, c->st>>>(dd, n, bands, tickets + 1);
         class_end(c, 4);
     }
     CK(cudaGetLastError());

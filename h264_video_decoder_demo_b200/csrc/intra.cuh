@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "residual.cuh"
 #include "residual_kernel.cuh"
+#include "wavefront.cuh"
 
 struct IntraWarpSmem {
     ResidualTile rt;
@@ -374,23 +375,23 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     }
 }
 
-// Wavefront driver.  ticket: one counter per launch (zeroed by the host); tickets are handed out
-// picture-interleaved so that every row's dependency (same picture, row-1) holds a smaller ticket and
-// is therefore already resident or finished: no deadlock regardless of how CTAs are scheduled.
-__global__ void __launch_bounds__(128) k_intra(const PicDev *pics, int npics, int max_rows, int *ticket) {
-    __shared__ IntraWarpSmem sm[4];
+// Wavefront driver (see wavefront.cuh): one CTA per band of WF_ROWS MB rows, one warp per row.
+__global__ void __launch_bounds__(WF_THREADS, 2) k_intra(const PicDev *pics, int npics, int bands, int *ticket) {
+    __shared__ IntraWarpSmem sm[WF_ROWS];
+    __shared__ int s_prog[WF_ROWS];
+    __shared__ int s_ticket;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int t = 0;
-    if (lane == 0) t = atomicAdd(ticket, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= npics * max_rows) return;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
+    if (threadIdx.x < WF_ROWS) s_prog[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = s_ticket;
+    if (t >= npics * bands) return;
     const PicDev &P = pics[t % npics];
-    const int row = t / npics;
+    const int row = (t / npics) * WF_ROWS + warp;
     const int per = P.mbaff ? 2 : 1;
     const int rows = P.hmb / per, wmb = P.wmb;
     if (row >= rows) return;
-    int *prog = P.progress;             // [0][row]
-    int seen = row == 0 ? wmb : 0;
+    RowSync rs = rs_init(s_prog, warp, row, rows, P.progress, wmb);      // progress[0][row]
     for (int xb = 0; xb < wmb; xb += 32) {
         const int xl = xb + lane;
         int intra_here = 0;
@@ -399,15 +400,7 @@ __global__ void __launch_bounds__(128) k_intra(const PicDev *pics, int npics, in
         while (mask) {
             const int x = xb + __ffs(mask) - 1;
             mask &= mask - 1;
-            const int need = min(x + 2, wmb);
-            if (seen < need) {
-                if (lane == 0) {
-                    st_relaxed_flag(&prog[row], x);          // everything left of x is final: let the row below run on
-                    while ((seen = ld_acquire_flag(&prog[row - 1])) < need) __nanosleep(20);
-                }
-                seen = __shfl_sync(0xffffffffu, seen, 0);
-                __threadfence();
-            }
+            rs_wait(rs, min(x + 2, wmb), x, lane);
             for (int s = 0; s < per; s++) {
                 const int a = (row * wmb + x) * per + s;
                 const H264B2MbInfo I = P.info[a];
@@ -415,11 +408,8 @@ __global__ void __launch_bounds__(128) k_intra(const PicDev *pics, int npics, in
                     if (P.mbaff) intra_mb<false>(P, a, I, lane, sm[warp]); else intra_mb<true>(P, a, I, lane, sm[warp]);
                 }
             }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_relaxed_flag(&prog[row], x + 1);
+            rs_publish(rs, x + 1, lane);
         }
     }
-    __syncwarp();
-    if (lane == 0) st_relaxed_flag(&prog[row], wmb);
+    rs_publish(rs, wmb, lane);
 }

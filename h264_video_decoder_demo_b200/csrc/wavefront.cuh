@@ -1,0 +1,87 @@
+// wavefront.cuh — row-progress synchronisation of the two macroblock-wavefront kernels (k_intra, k_deblock).
+//
+// A picture is cut into BANDS of WF_ROWS consecutive MB rows (pair rows under MBAFF); one CTA owns one band
+// and each of its warps owns one row.  Row r may work on column x once row r-1 has published progress
+// >= min(x+2, width) (left, top, top-left and top-right neighbours final).
+//   * rows inside a band hand over through SHARED-memory counters (fence.cta + volatile store: tens of cycles);
+//   * only the first row of a band waits on a GLOBAL counter written (st.release.gpu) by the last row of the
+//     band above, which lives in another CTA, possibly on another SM.
+// CTAs take (band, picture) tickets from an atomic counter, picture-interleaved and band-major, so the CTA a
+// band waits for always holds a smaller ticket and is already resident or finished: no deadlock however the
+// hardware schedules CTAs.  Samples always travel through global memory (L2).
+#pragma once
+#include <cuda_runtime.h>
+
+#define WF_ROWS 16                       // rows (warps) per band CTA
+#define WF_THREADS (WF_ROWS * 32)
+#ifndef WF_POLL_NS
+#define WF_POLL_NS 100                  // waiting warps sleep between polls so they do not steal issue slots from working warps
+#endif
+
+__device__ __forceinline__ int ld_relaxed_flag(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+struct RowSync {
+    volatile int *s_above;   // shared counter of the row above (same band), or nullptr
+    volatile int *s_mine;    // shared counter of this row
+    int *g_above;            // global counter of the row above (other band), or nullptr when this is row 0
+    int *g_mine;             // global counter of this row, or nullptr when no other band reads it
+    int seen;                // last observed progress of the row above
+    int width;
+};
+
+__device__ __forceinline__ RowSync rs_init(int *s_prog, int warp, int row, int rows, int *g_prog, int width) {
+    RowSync r;
+    r.s_mine = s_prog + warp;
+    r.s_above = warp > 0 ? s_prog + warp - 1 : nullptr;
+    r.g_above = (warp == 0 && row > 0) ? g_prog + row - 1 : nullptr;
+    r.g_mine = (warp == WF_ROWS - 1 && row + 1 < rows) ? g_prog + row : nullptr;
+    r.seen = row == 0 ? width : 0;
+    r.width = width;
+    return r;
+}
+
+// publish "columns < v of this row are final".  Call with the whole warp converged.
+__device__ __forceinline__ void rs_publish(RowSync &r, int v, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        *r.s_mine = v;
+        if (r.g_mine) st_release_gpu(r.g_mine, v);
+    }
+}
+
+// block until the row above has published >= need; `mine` = what this row can publish meanwhile
+__device__ __forceinline__ void rs_wait(RowSync &r, int need, int mine, int lane) {
+    if (r.seen >= need) return;
+    if (lane == 0) {
+        *r.s_mine = mine;                          // nothing of ours is pending: everything left of `mine` was published with a fence
+        if (r.g_mine) st_release_gpu(r.g_mine, mine);
+        int s;
+        if (r.s_above) { while ((s = *r.s_above) < need) __nanosleep(WF_POLL_NS); }
+        else { while ((s = ld_relaxed_flag(r.g_above)) < need) __nanosleep(2 * WF_POLL_NS); __threadfence(); }
+        r.seen = s;
+    }
+    r.seen = __shfl_sync(0xffffffffu, r.seen, 0);
+    __threadfence_block();
+    __syncwarp();
+}
+
+// non-blocking variant: true when the row above has already published >= need
+__device__ __forceinline__ bool rs_try(RowSync &r, int need, int lane) {
+    if (r.seen >= need) return true;
+    int s = 0;
+    if (lane == 0) s = r.s_above ? *r.s_above : ld_relaxed_flag(r.g_above);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (s < need) return false;
+    r.seen = s;
+    if (r.s_above) __threadfence_block(); else __threadfence();
+    __syncwarp();
+    return true;
+}
