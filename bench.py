@@ -176,11 +176,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--streams", type=int, default=64, help="concurrent replicas of the stream per GPU")
+    ap.add_argument("--streams", type=int, default=128, help="concurrent replicas of the stream per GPU")
     ap.add_argument("--workload", default="B_frames.cabac", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", default="full", choices=["full", "h2d", "d2h"], help="diagnostic: which PCIe legs the e2e loop includes")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--max-pictures", type=int, default=None)
     args = ap.parse_args()
@@ -310,26 +311,34 @@ def main():
 
         def e2e_step():
             for i, b in enumerate(host_batches):
-                eng.submit_prepared_host(b)
-                eng.read_pictures_async(sids, [dst[i]] * S, out_ptrs[i % nbuf])
+                if args.e2e_mode == "d2h":
+                    eng.submit_prepared(batches[i])
+                else:
+                    eng.submit_prepared_host(b)
+                if args.e2e_mode != "h2d":
+                    eng.read_pictures_async(sids, [dst[i]] * S, out_ptrs[i % nbuf])
 
         e2e_step()
         eng.sync()
         # the frames that came back are the reference's frames
         last = (npic - 1) % nbuf
         from h264_video_decoder_demo_b200 import abi
-        for s in (0, S - 1):
+        for s in ((0, S - 1) if args.e2e_mode != "h2d" else ()):
             if abi.checksum(out_host[last][s * eng.frame_bytes:(s + 1) * eng.frame_bytes].tobytes()) != rp.pictures[-1].sum_post:
                 raise SystemExit("PARITY FAILURE in the e2e path")
         sharding.barrier()
+        eng.timer_start()
         t0 = time.time()
         for _ in range(args.e2e_steps):
             e2e_step()
         eng.sync()
         t1 = sharding.max_over_ranks(time.time() - t0)
+        e2e_dev_ms = eng.timer_stop()
+        e2e_kt = eng.kernel_times()
         e2e = {"value": round(S * npic * args.e2e_steps * world / t1, 1), "unit": UNIT,
                "h2d_bytes_per_step": int(sum(p.nbytes() for p in rp.pictures) * S), "d2h_bytes_per_step": int(npic * S * eng.frame_bytes),
-               "steps": args.e2e_steps, "timing": "host wall clock around submit+read-back of every picture, synchronised on both sides, max over ranks"}
+               "steps": args.e2e_steps, "device_ms_per_step": round(e2e_dev_ms / args.e2e_steps, 1),
+               "kernel_ms_per_step": {k: round(v["ms"] / args.e2e_steps, 1) for k, v in e2e_kt.items()}, "timing": "host wall clock around submit+read-back of every picture, synchronised on both sides, max over ranks"}
 
     # ---- CPU baseline: the unmodified reference on one host core (rank 0, N=1 only)
     cpu = None

@@ -8,7 +8,7 @@
 #include "h264_recon_b200.h"
 
 // One entry per picture of a submitted batch.  All pointers are device pointers.
-struct PicDev {
+struct alignas(16) PicDev {
     const H264B2MbInfo   *info;
     const uint64_t       *modes;
     const uint32_t       *coef_off;
@@ -26,7 +26,9 @@ struct PicDev {
     int wmb, hmb, mbaff, cqp0, cqp1;
     int deblock_enable, deblock_stop;
     int n_weights, reserved;
+    int pad_[2];                       // sizeof(PicDev) is a multiple of 16: the batch prologue copies it as uint4
 };
+static_assert(sizeof(PicDev) % 16 == 0, "PicDev must be a multiple of 16 bytes");
 
 __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }

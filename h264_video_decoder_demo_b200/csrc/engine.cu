@@ -45,6 +45,20 @@ __global__ void k_checksum(const uint8_t *const *surf, size_t nwords, unsigned l
     if ((threadIdx.x & 31) == 0) atomicAdd(&out[blockIdx.y], acc);
 }
 
+// Batch prologue: pull the picture descriptors out of mapped pinned host memory and zero the wavefront
+// counters.  A kernel, not cudaMemcpyAsync/cudaMemsetAsync: copy-engine work queued on the launch stream
+// would wait behind the bulk H2D/D2H transfers of neighbouring batches (measured: +4 ms per batch).
+__global__ void k_prologue(const uint4 *src, uint4 *dst, int n16, int *progress, int nprog) {
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < nprog; i += blockDim.x) progress[i] = 0;
+}
+// snapshot n surfaces into the read-back staging buffer (same reason: keep the copy engines for PCIe)
+__global__ void k_snapshot(const uint8_t *const *src, uint8_t *dst, size_t n16) {
+    const uint4 *s = (const uint4 *)src[blockIdx.y];
+    uint4 *d = (uint4 *)dst + (size_t)blockIdx.y * n16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
 // ------------------------------------------------------------------ context
 enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 6 };
 
@@ -59,7 +73,7 @@ struct H264B2Context {
     int16_t *ls_flat;         // ls4 [2][2][6][16] then ls8 [2][2][6][64]
     cudaStream_t st, st_h2d, st_d2h;
     // descriptor ring
-    PicDev *h_desc, *d_desc;
+    PicDev *h_desc, *h_desc_dev, *d_desc;     // h_desc: mapped pinned host memory, h_desc_dev: its device alias
     cudaEvent_t desc_ev[DESC_RING];
     int desc_next;
     // host-submit staging: device arena slots
@@ -69,12 +83,35 @@ struct H264B2Context {
     // read-back staging
     uint8_t *out_stage[2]; size_t out_cap[2]; cudaEvent_t out_ready[2], out_done[2]; int out_next;
     uint8_t **d_ptrs; unsigned long long *d_sums; unsigned long long *h_sums; uint8_t **h_ptrs;
+    uint8_t **h_snap[2], **h_snap_dev[2];     // mapped pinned pointer lists for k_snapshot
     // timing
     cudaEvent_t t0, t1;
     int timing;
     cudaEvent_t *ev; int ev_used; int ev_class[EV_POOL / 2];
     float class_ms[KCLASSES]; long long class_launches[KCLASSES];
+    // optional timeline trace (H264B2_TRACE=path): per host submit, events at H2D start/end and compute start/end
+    int trace; int trace_n; cudaEvent_t trace_ev[256][4]; const char *trace_path;
 };
+
+static void trace_mark(H264B2Context *c, int which, cudaStream_t s) {
+    if (!c->trace || c->trace_n >= 256) return;
+    cudaEvent_t &e = c->trace_ev[c->trace_n][which];
+    if (!e) cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+}
+static void trace_dump(H264B2Context *c) {
+    if (!c->trace || c->trace_n < 2) return;
+    FILE *f = fopen(c->trace_path, "a");
+    if (!f) return;
+    fprintf(f, "# batch h2d_start h2d_end compute_start compute_end (ms since first H2D start)\n");
+    for (int i = 0; i < c->trace_n; i++) {
+        float t[4];
+        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], c->trace_ev[0][0], c->trace_ev[i][k]);
+        fprintf(f, "%d %.3f %.3f %.3f %.3f\n", i, t[0], t[1], t[2], t[3]);
+    }
+    fclose(f);
+    c->trace_n = 0;
+}
 
 static const uint8_t h_zz4[16] = {0,1,4,8, 5,2,3,6, 9,12,13,10, 7,11,14,15};
 static const uint8_t h_fs4[16] = {0,4,1,8, 12,5,9,13, 2,6,10,14, 3,7,11,15};
@@ -154,7 +191,12 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
-    CK(cudaMallocHost(&c->h_desc, sizeof(PicDev) * n_streams * DESC_RING));
+    CK(cudaHostAlloc(&c->h_desc, sizeof(PicDev) * n_streams * DESC_RING, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&c->h_desc_dev, c->h_desc, 0));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaHostAlloc(&c->h_snap[i], sizeof(uint8_t *) * n_streams, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void **)&c->h_snap_dev[i], c->h_snap[i], 0));
+    }
     CK(cudaMalloc(&c->d_desc, sizeof(PicDev) * n_streams * DESC_RING));
     for (int i = 0; i < DESC_RING; i++) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < NSLOT; i++) { CK(cudaEventCreateWithFlags(&c->h2d_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming)); }
@@ -166,6 +208,8 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaEventCreate(&c->t0)); CK(cudaEventCreate(&c->t1));
     c->ev = (cudaEvent_t *)calloc(EV_POOL, sizeof(cudaEvent_t));
     if (init_tables(c)) return -10;
+    c->trace_path = getenv("H264B2_TRACE");
+    c->trace = c->trace_path != nullptr;
     *out = c;
     return 0;
 }
@@ -174,7 +218,7 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     if (!c) return fail(-1, "null context");
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc);
+    cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_snap[0]); cudaFreeHost(c->h_snap[1]);
     for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->compute_done[i]); }
     for (int i = 0; i < 2; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
     for (int i = 0; i < DESC_RING; i++) cudaEventDestroy(c->desc_ev[i]);
@@ -244,11 +288,11 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.n_weights = p.n_weights; d.reserved = 0;
         any_inter |= p.has_inter; any_deblock |= p.deblock_enable;
     }
-    CK(cudaMemcpyAsync(dd, hd, sizeof(PicDev) * n, cudaMemcpyHostToDevice, c->st));
-    CK(cudaEventRecord(c->desc_ev[ring], c->st));
     int *tickets = c->progress + (c->progress_ints - DESC_RING * 2) + ring * 2;
     class_begin(c, 0);
-    CK(cudaMemsetAsync(c->progress, 0, c->progress_ints * 4, c->st));
+    static_assert(sizeof(PicDev) % 16 == 0, "PicDev must be a multiple of 16 bytes");
+    k_prologue<<<1, 256, 0, c->st>>>((const uint4 *)(c->h_desc_dev + (size_t)ring * c->n_streams), (uint4 *)dd, (int)(sizeof(PicDev) * n / 16), c->progress, (int)c->progress_ints);
+    CK(cudaEventRecord(c->desc_ev[ring], c->st));
     for (int i = 0; i < n; i++) if (pics[i].clear_surface) CK(cudaMemsetAsync(hd[i].dst, 0, c->frame_bytes, c->st));
     class_end(c, 0);
     class_begin(c, 5);
@@ -318,6 +362,7 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
         CK(cudaMalloc(&c->arena[slot], c->arena_cap[slot]));
     }
     CK(cudaStreamWaitEvent(c->st_h2d, c->compute_done[slot], 0));
+    trace_mark(c, 0, c->st_h2d);
     // copy: merge spans that are adjacent in host memory (same relative alignment kept)
     size_t off = 0;
     size_t i = 0;
@@ -333,10 +378,14 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
         i = j + 1;
     }
     CK(cudaEventRecord(c->h2d_done[slot], c->st_h2d));
+    trace_mark(c, 1, c->st_h2d);
     CK(cudaStreamWaitEvent(c->st, c->h2d_done[slot], 0));
+    trace_mark(c, 2, c->st);
     r = launch_batch(c, n_pics, sids, dev.data());
     if (r) return r;
     CK(cudaEventRecord(c->compute_done[slot], c->st));
+    trace_mark(c, 3, c->st);
+    if (c->trace && c->trace_n < 256) c->trace_n++;
     return 0;
 }
 
@@ -353,6 +402,7 @@ extern "C" int h264b2_sync(H264B2Context *c) {
     if (!c) return fail(-1, "null context");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->st_h2d)); CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_d2h));
+    trace_dump(c);
     return 0;
 }
 extern "C" int h264b2_read_picture(H264B2Context *c, int sid, int surface, uint8_t *host) {
@@ -385,11 +435,10 @@ extern "C" int h264b2_read_pictures_async(H264B2Context *c, int n, const int32_t
         c->out_cap[s] = (size_t)c->n_streams * c->frame_bytes;
         CK(cudaMalloc(&c->out_stage[s], c->out_cap[s]));
     }
-    CK(cudaStreamWaitEvent(c->st, c->out_done[s], 0));
-    for (int i = 0; i < n; i++) {
-        uint8_t *p; int r = surf_ptr(c, sids[i], surfaces[i], &p); if (r) return r;
-        CK(cudaMemcpyAsync(c->out_stage[s] + (size_t)i * c->frame_bytes, p, c->frame_bytes, cudaMemcpyDeviceToDevice, c->st));
-    }
+    CK(cudaEventSynchronize(c->out_done[s]));     // the pointer list of this slot is free again (2 read-backs ago)
+    for (int i = 0; i < n; i++) { int r = surf_ptr(c, sids[i], surfaces[i], &c->h_snap[s][i]); if (r) return r; }
+    k_snapshot<<<dim3(32, n), 256, 0, c->st>>>(c->h_snap_dev[s], c->out_stage[s], c->frame_bytes / 16);
+    CK(cudaGetLastError());
     CK(cudaEventRecord(c->out_ready[s], c->st));
     CK(cudaStreamWaitEvent(c->st_d2h, c->out_ready[s], 0));
     for (int i = 0; i < n; i++)

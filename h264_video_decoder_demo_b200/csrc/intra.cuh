@@ -213,22 +213,17 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
             put_px(px, have, pred, r);
         }
     };
-    {   // stage this MB's residual (k_residual output) as a raster tile: luma 16x16, Cb 8x8, Cr 8x8
-        const int16_t *src = P.res + (size_t)a * RES_MB_STRIDE;
+    {   // stage this MB's residual (k_residual wrote all 24 blocks of an intra MB) as a raster tile: luma 16x16, Cb 8x8, Cr 8x8
+        const uint32_t *src = (const uint32_t *)(P.res + (size_t)a * RES_MB_STRIDE);
         const int hasres = mb_has_residual(I);
-        const int t8eff = (I.flags & H264B2_MBF_T8x8) && cls != H264B2_MB_I16x16;
-        for (int e = lane; e < 384; e += 32) {
-            const int slot = e >> 4, inner = e & 15;
-            int v = 0, dsti;
-            if (slot < 16) {
-                if (hasres && luma_slot_coded(I.coef_mask, cls, t8eff, slot)) v = src[e];
-                dsti = ((slot >> 2) * 4 + (inner >> 2)) * 16 + (slot & 3) * 4 + (inner & 3);
-            } else {
-                const int c = (slot - 16) >> 2, b = (slot - 16) & 3;
-                if (hasres && chroma_blk_coded(I.coef_mask, c, b)) v = src[e];
-                dsti = 256 + c * 64 + ((b >> 1) * 4 + (inner >> 2)) * 8 + (b & 1) * 4 + (inner & 3);
-            }
-            S.rt.res[dsti] = (int16_t)v;
+#pragma unroll
+        for (int t = 0; t < 6; t++) {
+            const int w = lane + 32 * t, e = 2 * w, slot = e >> 4, inner = e & 15;
+            const uint32_t v = hasres ? src[w] : 0u;
+            int dsti;
+            if (slot < 16) dsti = ((slot >> 2) * 4 + (inner >> 2)) * 16 + (slot & 3) * 4 + (inner & 3);
+            else { const int c = (slot - 16) >> 2, b = (slot - 16) & 3; dsti = 256 + c * 64 + ((b >> 1) * 4 + (inner >> 2)) * 8 + (b & 1) * 4 + (inner & 3); }
+            *(uint32_t *)&S.rt.res[dsti] = v;
         }
         __syncwarp();
     }
@@ -325,16 +320,17 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
         }
     }
 
-    // chroma, both components (PB:2076)
-    const int cmode = (I.pred16_chroma >> 2) & 3;
-    for (int comp = 1; comp <= 2; comp++) {
+    // chroma (PB:2076): the two components are independent, so lanes 0-15 predict Cb while lanes 16-31 predict Cr
+    {
+        const int cmode = (I.pred16_chroma >> 2) & 3;
+        const int comp = 1 + (lane >> 4), hl = lane & 15;
+        int *nbc = S.nb + 17 * (lane >> 4);              // [0] corner, [1..8] top, [9..16] left
         __syncwarp();
-        if (lane < 8) S.nb[1 + lane] = sample(lane, -1, comp);
-        else if (lane < 16) S.nb[9 + lane - 8] = sample(-1, lane - 8, comp);
-        else if (lane == 16) S.nb[0] = sample(-1, -1, comp);
+        if (hl < 8) nbc[1 + hl] = sample(hl, -1, comp); else nbc[9 + hl - 8] = sample(-1, hl - 8, comp);
+        if (hl == 0) nbc[0] = sample(-1, -1, comp);
         __syncwarp();
-        const int *top = S.nb + 1, *left = S.nb + 9;
-        const int corner = S.nb[0];
+        const int *top = nbc + 1, *left = nbc + 9;
+        const int corner = nbc[0];
         const int16_t *cres = res + 256 + (comp - 1) * 64;
         int topok = 1, leftok = 1;
         for (int i = 0; i < 8; i++) { if (top[i] < 0) topok = 0; if (left[i] < 0) leftok = 0; }
@@ -347,7 +343,7 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
             for (int i = 0; i < 4; i++) { Hh += (i + 1) * (top[4 + i] - (2 - i >= 0 ? top[2 - i] : corner)); V += (i + 1) * (left[4 + i] - (2 - i >= 0 ? left[2 - i] : corner)); }
             aa = 16 * (left[7] + top[7]); bb = (34 * Hh + 32) >> 6; cc = (34 * V + 32) >> 6;
         }
-        for (int i = lane; i < 64; i += 32) {
+        for (int i = hl; i < 64; i += 16) {
             const int x = i & 7, y = i >> 3;
             int pred;
             if (cmode == 0) {

@@ -59,6 +59,9 @@ __global__ void __launch_bounds__(256) k_residual(const PicDev *pics) {
     const int16_t *ls4 = P.ls4 + ((inter * 2 + sf) * 6) * 16;   // chroma uses the luma list of the same MB (Q7)
     const int16_t *ls8 = P.ls8 + ((inter * 2 + sf) * 6) * 64;
     int16_t *out = P.res + (size_t)a * RES_MB_STRIDE;
+    // intra MBs get ALL 24 blocks written (zeros where nothing is coded): k_intra stages the whole tile with
+    // plain vector loads; inter MBs only get their coded blocks (k_inter tests the mask per block)
+    const int full = !inter;
 
     if (t8) {
         // ---- luma 8x8: 8 lanes per block
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(256) k_residual(const PicDev *pics) {
                 if (up) d[j0] = got; else d[j0 | k] = got;
             }
         }
-        if (coded) {
+        if (coded || full) {
             butterfly8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
             // lane i owns column i of 8x8 block b: scatter into the raster 4x4 slots
             const int xq = (b & 1) * 8 + i, yq = (b >> 1) * 8;
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256) k_residual(const PicDev *pics) {
 #pragma unroll
             for (int j = 0; j < 16; j++) if (j == idx) dc = dcY[j];
         }
-        if (lv || (is16 && (m & H264B2_CM_LUMA_DC))) {
+        if (lv || (is16 && (m & H264B2_CM_LUMA_DC)) || full) {
             int16_t r[16];
             resid4x4_thread(lv, dc, is16, qp, ls4, sf, r, 4);
             store_blk16(out + ((blk_y(b) >> 2) * 4 + (blk_x(b) >> 2)) * 16, r);
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(256) k_residual(const PicDev *pics) {
     // ---- chroma: lanes 16..23 (c = Cb/Cr, b = block)
     if (lane >= 16 && lane < 24) {
         const int c = (lane - 16) >> 2, b = (lane - 16) & 3;
-        if (chroma_blk_coded(m, c, b)) {
+        if (chroma_blk_coded(m, c, b) || full) {
             const int qpc = chroma_qp(P, qp, c);
             int dc = 0;
             if (m & H264B2_CM_CHROMA_DC) {                   // PB:3989
