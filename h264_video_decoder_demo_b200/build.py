@@ -13,6 +13,28 @@ SOURCES = ["engine.cu"]
 HEADERS = ["common.cuh", "residual.cuh", "residual_kernel.cuh", "inter.cuh", "intra.cuh", "deblock.cuh", "deblock_fast.cuh", "wavefront.cuh"]
 
 
+HOST_LIB = os.path.join(_PKG, "libh264b2_host.so")
+HOST_CLI = os.path.join(_PKG, "h264b2_decode")
+HOST_SRC = os.path.join(CSRC, "host", "H264VideoDecoderB200.cpp")
+CLI_SRC = os.path.join(_ROOT, "tools", "h264b2_decode.cpp")
+
+
+def build_host(force=False):
+    """The C++ host facade (CH264VideoDecoderB200) and its CLI: plain g++ over the C ABI, rpath = $ORIGIN."""
+    deps = [HOST_SRC, CLI_SRC, os.path.join(_ROOT, "include", "H264VideoDecoderB200.h"), os.path.join(_ROOT, "include", "h264_recon_b200.h"), LIB]
+    if not force and all(os.path.exists(x) and os.path.getmtime(x) >= max(os.path.getmtime(d) for d in deps) for x in (HOST_LIB, HOST_CLI)):
+        return HOST_LIB
+    inc = ["-I", os.path.join(_ROOT, "include")]
+    common = ["-O2", "-std=c++11", "-fPIC", "-Wall"] + inc
+    for cmd in (["g++"] + common + ["-shared", "-o", HOST_LIB, HOST_SRC, "-L", _PKG, "-lh264b2", "-Wl,-rpath,$ORIGIN"],
+                ["g++"] + common + ["-o", HOST_CLI, CLI_SRC, "-L", _PKG, "-lh264b2_host", "-lh264b2", "-Wl,-rpath,$ORIGIN"]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed building the host facade")
+    return HOST_LIB
+
+
 def _nvcc():
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -30,6 +52,7 @@ def needs_build():
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        build_host()
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-warn-spills",
@@ -40,6 +63,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libh264b2.so")
+    build_host(force=True)
     return LIB
 
 
