@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-warn-spills",
-           "-I", os.path.join(_ROOT, "include"), "-I", CSRC,
+           "-I", os.path.join(_ROOT, "include"), "-I", CSRC] + os.environ.get("H264B2_NVCC_FLAGS", "").split() + [
            "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:

@@ -237,7 +237,7 @@ __device__ inline void deblock_mb(const PicDev &P, int a, int lane) {
 
 #include "deblock_fast.cuh"
 
-__global__ void __launch_bounds__(WF_THREADS, 2) k_deblock(const PicDev *pics, int npics, int bands, int *ticket) {
+__global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_deblock(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ DbTile tiles[WF_ROWS];
     __shared__ int s_prog[WF_ROWS];
     __shared__ int s_ticket;

@@ -60,7 +60,7 @@ __global__ void k_snapshot(const uint8_t *const *src, uint8_t *dst, size_t n16) 
 }
 
 // ------------------------------------------------------------------ context
-enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 6 };
+enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 6, MAX_GROUPS = 8 };
 
 struct H264B2Context {
     int device, n_streams, spp, wmb, hmb, nmb;
@@ -72,6 +72,12 @@ struct H264B2Context {
     size_t progress_ints;
     int16_t *ls_flat;         // ls4 [2][2][6][16] then ls8 [2][2][6][64]
     cudaStream_t st, st_h2d, st_d2h;
+    // A batch is cut into `groups` picture groups whose kernel sequences run on separate streams, forked from and
+    // joined back into `st`: the latency-bound wavefront kernels of one group overlap the issue-bound kernels
+    // (and the wavefronts) of the others.
+    int groups, group_min;
+    cudaStream_t st_g[MAX_GROUPS];
+    cudaEvent_t fork_ev, join_ev[MAX_GROUPS];
     // descriptor ring
     PicDev *h_desc, *h_desc_dev, *d_desc;     // h_desc: mapped pinned host memory, h_desc_dev: its device alias
     cudaEvent_t desc_ev[DESC_RING];
@@ -186,11 +192,21 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaMemset(c->surfaces, 0, total + (size_t)width_mbs * 64));
     CK(cudaMalloc(&c->bs, (size_t)n_streams * c->nmb * 65 * 4));
     CK(cudaMalloc(&c->res, (size_t)n_streams * c->nmb * RES_MB_STRIDE * 2));
-    c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 2;
+    c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 2 * MAX_GROUPS;
+    {
+        const char *g = getenv("H264B2_GROUPS"), *gm = getenv("H264B2_GROUP_MIN");
+        c->groups = g ? atoi(g) : 1;      // measured (S=128): 1 group 15.0k, 2 groups 14.0k, 4 groups 13.3k frames/s — the GPU is already issue-bound
+        if (c->groups < 1) c->groups = 1;
+        if (c->groups > MAX_GROUPS) c->groups = MAX_GROUPS;
+        c->group_min = gm ? atoi(gm) : 8;
+        if (c->group_min < 1) c->group_min = 1;
+    }
     CK(cudaMalloc(&c->progress, c->progress_ints * 4));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < MAX_GROUPS; i++) { CK(cudaStreamCreateWithFlags(&c->st_g[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming)); }
+    CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     CK(cudaHostAlloc(&c->h_desc, sizeof(PicDev) * n_streams * DESC_RING, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void **)&c->h_desc_dev, c->h_desc, 0));
     for (int i = 0; i < 2; i++) {
@@ -227,21 +243,23 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     free(c->ev);
     cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
     cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_d2h);
+    for (int i = 0; i < MAX_GROUPS; i++) { cudaStreamDestroy(c->st_g[i]); cudaEventDestroy(c->join_ev[i]); }
+    cudaEventDestroy(c->fork_ev);
     delete c;
     return 0;
 }
 
 // ------------------------------------------------------------------ timing helpers
-static void class_begin(H264B2Context *c, int cls) {
+static void class_begin(H264B2Context *c, int cls, cudaStream_t s) {
     if (!c->timing || c->ev_used + 2 > EV_POOL) return;
     for (int i = 0; i < 2; i++) if (!c->ev[c->ev_used + i]) cudaEventCreate(&c->ev[c->ev_used + i]);
     c->ev_class[c->ev_used / 2] = cls;
-    cudaEventRecord(c->ev[c->ev_used], c->st);
+    cudaEventRecord(c->ev[c->ev_used], s);
 }
-static void class_end(H264B2Context *c, int cls) {
+static void class_end(H264B2Context *c, int cls, cudaStream_t s) {
     c->class_launches[cls]++;
     if (!c->timing || c->ev_used + 2 > EV_POOL) return;
-    cudaEventRecord(c->ev[c->ev_used + 1], c->st);
+    cudaEventRecord(c->ev[c->ev_used + 1], s);
     c->ev_used += 2;
 }
 
@@ -288,33 +306,46 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.n_weights = p.n_weights; d.reserved = 0;
         any_inter |= p.has_inter; any_deblock |= p.deblock_enable;
     }
-    int *tickets = c->progress + (c->progress_ints - DESC_RING * 2) + ring * 2;
-    class_begin(c, 0);
-    static_assert(sizeof(PicDev) % 16 == 0, "PicDev must be a multiple of 16 bytes");
+    int *tickets = c->progress + (c->progress_ints - DESC_RING * 2 * MAX_GROUPS) + ring * 2 * MAX_GROUPS;
+    class_begin(c, 0, c->st);
     k_prologue<<<1, 256, 0, c->st>>>((const uint4 *)(c->h_desc_dev + (size_t)ring * c->n_streams), (uint4 *)dd, (int)(sizeof(PicDev) * n / 16), c->progress, (int)c->progress_ints);
     CK(cudaEventRecord(c->desc_ev[ring], c->st));
     for (int i = 0; i < n; i++) if (pics[i].clear_surface) CK(cudaMemsetAsync(hd[i].dst, 0, c->frame_bytes, c->st));
-    class_end(c, 0);
-    class_begin(c, 5);
-    k_residual<<<dim3((c->nmb + 7) / 8, n), 256, 0, c->st>>>(dd);
-    class_end(c, 5);
-    if (any_inter) {
-        class_begin(c, 1);
-        k_inter<<<dim3((c->nmb + 7) / 8, n), 128, 0, c->st>>>(dd);
-        class_end(c, 1);
-    }
+    class_end(c, 0, c->st);
+    int G = c->groups;
+    while (G > 1 && n / G < c->group_min) G--;
     const int bands = (c->hmb + WF_ROWS - 1) / WF_ROWS;
-    class_begin(c, 2);
-    k_intra<<<n * bands, WF_THREADS, 0, c->st>>>(dd, n, bands, tickets);
-    class_end(c, 2);
-    if (any_deblock) {
-        class_begin(c, 3);
-        k_bs<<<dim3((c->nmb + 7) / 8, n), 256, 0, c->st>>>(dd);
-        class_end(c, 3);
-        class_begin(c, 4);
-        k_deblock<<<n * bands, WF_THREADS, 0, c->st>>>(dd, n, bands, tickets + 1);
-        class_end(c, 4);
+    if (G > 1) CK(cudaEventRecord(c->fork_ev, c->st));
+    for (int g = 0; g < G; g++) {
+        const int b0 = (int)((long long)n * g / G), b1 = (int)((long long)n * (g + 1) / G), ng = b1 - b0;
+        if (ng <= 0) continue;
+        cudaStream_t sg = G > 1 ? c->st_g[g] : c->st;
+        if (G > 1) CK(cudaStreamWaitEvent(sg, c->fork_ev, 0));
+        int g_inter = 0, g_deblock = 0;
+        for (int i = b0; i < b1; i++) { g_inter |= pics[i].has_inter; g_deblock |= pics[i].deblock_enable; }
+        const PicDev *dg = dd + b0;
+        class_begin(c, 5, sg);
+        k_residual<<<dim3((c->nmb + 7) / 8, ng), 256, 0, sg>>>(dg);
+        class_end(c, 5, sg);
+        if (g_inter) {
+            class_begin(c, 1, sg);
+            k_inter<<<dim3((c->nmb + 7) / 8, ng), 128, 0, sg>>>(dg);
+            class_end(c, 1, sg);
+        }
+        class_begin(c, 2, sg);
+        k_intra<<<ng * bands, WF_THREADS, 0, sg>>>(dg, ng, bands, tickets + 2 * g);
+        class_end(c, 2, sg);
+        if (g_deblock) {
+            class_begin(c, 3, sg);
+            k_bs<<<dim3((c->nmb + 7) / 8, ng), 256, 0, sg>>>(dg);
+            class_end(c, 3, sg);
+            class_begin(c, 4, sg);
+            k_deblock<<<ng * bands, WF_THREADS, 0, sg>>>(dg, ng, bands, tickets + 2 * g + 1);
+            class_end(c, 4, sg);
+        }
+        if (G > 1) { CK(cudaEventRecord(c->join_ev[g], sg)); CK(cudaStreamWaitEvent(c->st, c->join_ev[g], 0)); }
     }
+    (void)any_inter; (void)any_deblock;
     CK(cudaGetLastError());
     return 0;
 }

@@ -211,7 +211,10 @@ __device__ __forceinline__ int weigh(const H264B2Weight &w, int c, int have0, in
 
 // grid: (ceil(n_mbs / 8), n_pics); block: 128 threads = 4 warps; warp w = 4x4-block row `by` of 8 consecutive
 // macroblock addresses, lane = (mb_in_group << 2) | bx.
-__global__ void __launch_bounds__(128) k_inter(const PicDev *pics) {
+#ifndef INTER_MIN_BLOCKS
+#define INTER_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *pics) {
     const PicDev &P = pics[blockIdx.y];
     const int lane = threadIdx.x & 31, by4 = threadIdx.x >> 5, bx4 = lane & 3;
     const int a = blockIdx.x * 8 + (lane >> 2);

@@ -372,7 +372,7 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
 }
 
 // Wavefront driver (see wavefront.cuh): one CTA per band of WF_ROWS MB rows, one warp per row.
-__global__ void __launch_bounds__(WF_THREADS, 2) k_intra(const PicDev *pics, int npics, int bands, int *ticket) {
+__global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ IntraWarpSmem sm[WF_ROWS];
     __shared__ int s_prog[WF_ROWS];
     __shared__ int s_ticket;

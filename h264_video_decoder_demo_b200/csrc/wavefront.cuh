@@ -12,7 +12,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef WF_ROWS
 #define WF_ROWS 16                       // rows (warps) per band CTA
+#endif
 #define WF_THREADS (WF_ROWS * 32)
 #ifndef WF_POLL_NS
 #define WF_POLL_NS 100                  // waiting warps sleep between polls so they do not steal issue slots from working warps

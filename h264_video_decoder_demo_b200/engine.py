@@ -58,7 +58,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             if not build_if_missing:
                 raise EngineError(f"{_build.LIB} is missing and there is no CPU fallback; run __graft_entry__.build()")
             _build.build()
-        lib = C.CDLL(_build.LIB)
+        lib = C.CDLL(os.environ.get("H264B2_LIB", _build.LIB))      # H264B2_LIB: A/B a differently compiled engine
         for name, (res, args) in _PROTOS.items():
             fn = getattr(lib, name)       # raises AttributeError if the library does not export it
             fn.restype, fn.argtypes = res, args
