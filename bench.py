@@ -296,7 +296,8 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get({"inter": "k_inter", "intra": "k_intra", "deblock": "k_deblock"}[dom], {}).get("dram_bytes_per_launch")
+        per_pic = tr.get({"inter": "k_inter", "intra": "k_intra", "deblock": "k_deblock"}[dom], {}).get("dram_bytes_per_picture")
+        traffic = int(per_pic * S) if per_pic else None      # per launch = per picture x pictures per launch
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": {"inter": "k_inter", "intra": "k_intra", "deblock": "k_bs+k_deblock"}[dom], "achieved": achieved, "peak": peak,
