@@ -375,6 +375,7 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
 __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ IntraWarpSmem sm[WF_ROWS];
     __shared__ int s_prog[WF_ROWS];
+    __shared__ uint32_t s_mask[WF_ROWS][2][8];
     __shared__ int s_ticket;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
@@ -388,15 +389,39 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
     const int rows = P.hmb / per, wmb = P.wmb;
     if (row >= rows) return;
     RowSync rs = rs_init(s_prog, warp, row, rows, P.progress, wmb);      // progress[0][row]
+    // Intra masks of this row and of the row above.  An intra MB only has to wait for the row above if one of its
+    // neighbours B, C, D there is itself intra: inter neighbours were completed by k_inter before this kernel
+    // started.  In P/B pictures, where intra MBs are scattered, this removes the false chains a plain
+    // "row above >= x+2" rule would build through unrelated macroblocks.
+    uint32_t *mine = s_mask[warp][0], *above = s_mask[warp][1];
+    const bool masks_ok = wmb <= 256;
+    for (int g = 0; g < 8 && masks_ok; g++) {
+        const int xl = g * 32 + lane;
+        int im = 0, ia = 0;
+        if (xl < wmb) for (int s = 0; s < per; s++) {
+            const int c = P.info[(row * wmb + xl) * per + s].mb_class; im |= (c >= H264B2_MB_I4x4 && c <= H264B2_MB_IPCM);
+            if (row > 0) { const int ca = P.info[((row - 1) * wmb + xl) * per + s].mb_class; ia |= (ca >= H264B2_MB_I4x4 && ca <= H264B2_MB_IPCM); }
+        }
+        const unsigned mm = __ballot_sync(0xffffffffu, im), ma = __ballot_sync(0xffffffffu, ia);
+        if (lane == 0) { mine[g] = mm; above[g] = ma; }
+    }
+    __syncwarp();
+    auto above_intra = [&](int x) -> bool { return x >= 0 && x < wmb && ((above[x >> 5] >> (x & 31)) & 1u); };
     for (int xb = 0; xb < wmb; xb += 32) {
-        const int xl = xb + lane;
-        int intra_here = 0;
-        if (xl < wmb) for (int s = 0; s < per; s++) { const int c = P.info[(row * wmb + xl) * per + s].mb_class; intra_here |= (c >= H264B2_MB_I4x4 && c <= H264B2_MB_IPCM); }
-        unsigned mask = __ballot_sync(0xffffffffu, intra_here);
+        unsigned mask;
+        if (masks_ok) mask = mine[xb >> 5];
+        else {
+            const int xl = xb + lane;
+            int intra_here = 0;
+            if (xl < wmb) for (int s = 0; s < per; s++) { const int c = P.info[(row * wmb + xl) * per + s].mb_class; intra_here |= (c >= H264B2_MB_I4x4 && c <= H264B2_MB_IPCM); }
+            mask = __ballot_sync(0xffffffffu, intra_here);
+        }
         while (mask) {
             const int x = xb + __ffs(mask) - 1;
             mask &= mask - 1;
-            rs_wait(rs, min(x + 2, wmb), x, lane);
+            int need = min(x + 2, wmb);
+            if (masks_ok) need = above_intra(x + 1) ? x + 2 : above_intra(x) ? x + 1 : above_intra(x - 1) ? x : 0;
+            rs_wait(rs, need, x, lane);
             for (int s = 0; s < per; s++) {
                 const int a = (row * wmb + x) * per + s;
                 const H264B2MbInfo I = P.info[a];
