@@ -40,6 +40,7 @@ WORKLOADS = {
     "no_B_frames.cabac": "HeavyHand_1080p.no_B_frames.cabac.no_tff",
     "gop121": "gop121.naluCnt453",
 }
+MIXED = ["B_frames.cabac", "B_frames_4.no_cabac", "tff", "no_B_frames.cabac", "gop121"]     # BASELINE config 5: all bundled variants, round-robin
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
@@ -177,7 +178,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=128, help="concurrent replicas of the stream per GPU")
-    ap.add_argument("--workload", default="B_frames.cabac", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="B_frames.cabac", choices=sorted(WORKLOADS) + ["mixed"],
+                    help="one bundled stream replicated S times, or 'mixed' = all five bundled variants dealt round-robin over the S streams")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
@@ -185,7 +187,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--max-pictures", type=int, default=None)
     args = ap.parse_args()
-    stem = WORKLOADS[args.workload]
+    stems = [WORKLOADS[w] for w in (MIXED if args.workload == "mixed" else [args.workload])]
+    stem = stems[0]
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
@@ -213,28 +216,44 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    path, is_full = find_replay(stem)
     S = args.streams
     eng_probe = engine.load_library()   # fails loudly when the CUDA library is missing: no fallback
     del eng_probe
-    raw = replay.read_replay_bytes(path)
-    rp0 = replay.parse_replay(raw, path, args.max_pictures)
-    eng = engine.Engine(local_rank, S, rp0.width_mbs, rp0.height_mbs)
-    # page-locked copy of the container: the e2e leg DMAs every picture's arrays straight from it
-    pinned = eng.pinned_array(len(raw))
-    pinned[:] = np.frombuffer(raw, dtype=np.uint8)
-    del raw
-    rp = replay.parse_replay(pinned, path, args.max_pictures)
-    npic = len(rp.pictures)
-    # resident replicas: one distinct HBM copy of the SoA per stream
-    rs = [engine.ResidentStream(eng, rp)]
-    for _ in range(1, S):
-        rs.append(rs[0].clone())
+    # one variant per distinct bitstream: page-locked copy of its container (the e2e leg DMAs every picture's arrays
+    # straight from it) + replicas resident in HBM, one distinct copy of the SoA per stream
+    variants, is_full, eng = [], True, None
+    for st in stems:
+        path, full = find_replay(st)
+        is_full &= full
+        raw = replay.read_replay_bytes(path)
+        if eng is None:
+            rp0 = replay.parse_replay(raw, path, 1)
+            eng = engine.Engine(local_rank, S, rp0.width_mbs, rp0.height_mbs)
+        pinned = eng.pinned_array(len(raw))
+        pinned[:] = np.frombuffer(raw, dtype=np.uint8)
+        del raw
+        rpv = replay.parse_replay(pinned, path, args.max_pictures)
+        variants.append({"rp": rpv, "host_params": [replay.pic_params(rpv, pic) for pic in rpv.pictures], "rs": None})
     sids = list(range(S))
-    batches = [eng.prepare(sids, [rs[s].params[i] for s in sids]) for i in range(npic)]
-    host_params = [replay.pic_params(rp, pic) for pic in rp.pictures]
-    host_batches = [eng.prepare(sids, [host_params[i]] * S) for i in range(npic)]
-    dst = [pic.dst_surface for pic in rp.pictures]
+    var_of = [s % len(variants) for s in sids]
+    rs = []
+    for s in sids:
+        v = variants[var_of[s]]
+        if v["rs"] is None:
+            v["rs"] = engine.ResidentStream(eng, v["rp"])
+            rs.append(v["rs"])
+        else:
+            rs.append(v["rs"].clone())
+    rp = variants[0]["rp"]
+    npic = max(len(v["rp"].pictures) for v in variants)          # submits per step; shorter streams wrap to their IDR
+
+    def pic_of(s, i):
+        return i % len(variants[var_of[s]]["rp"].pictures)
+
+    batches = [eng.prepare(sids, [rs[s].params[pic_of(s, i)] for s in sids]) for i in range(npic)]
+    host_batches = [eng.prepare(sids, [variants[var_of[s]]["host_params"][pic_of(s, i)] for s in sids]) for i in range(npic)]
+    dst = [[variants[var_of[s]]["rp"].pictures[pic_of(s, i)].dst_surface for s in sids] for i in range(npic)]
+    want = [[variants[var_of[s]]["rp"].pictures[pic_of(s, i)].sum_post for s in sids] for i in range(npic)]
 
     def step():
         for b in batches:
@@ -245,9 +264,9 @@ def main():
         if w == max(args.warmup, 1) - 1:
             for i, b in enumerate(batches):
                 eng.submit_prepared(b)
-                sums = eng.checksums(sids, [dst[i]] * S)
-                if any(x != rp.pictures[i].sum_post for x in sums):
-                    raise SystemExit(f"PARITY FAILURE: picture {i}: {sum(x != rp.pictures[i].sum_post for x in sums)} of {S} streams differ from the reference")
+                sums = eng.checksums(sids, dst[i])
+                if sums != want[i]:
+                    raise SystemExit(f"PARITY FAILURE: submit {i}: {sum(x != y for x, y in zip(sums, want[i]))} of {S} streams differ from the reference")
         else:
             step()
     eng.sync()
@@ -270,13 +289,12 @@ def main():
     pictures_per_rank = S * npic * args.steps
     value = pictures_per_rank * world / (ms_max / 1000.0)
     # final state check: the last picture of every stream still equals the reference
-    sums = eng.checksums(sids, [dst[-1]] * S)
-    if any(x != rp.pictures[-1].sum_post for x in sums):
+    if eng.checksums(sids, dst[-1]) != want[-1]:
         raise SystemExit("PARITY FAILURE after the timed region")
 
     # ---- roofline of the dominant kernel
-    ab = algorithmic_bytes(rp)
-    per_step = {k: sum(a[k] for a in ab) * S for k in ("inter", "intra", "deblock")}
+    abv = [algorithmic_bytes(v["rp"]) for v in variants]
+    per_step = {k: sum(abv[var_of[s]][pic_of(s, i)][k] for s in sids for i in range(npic)) for k in ("inter", "intra", "deblock")}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -320,7 +338,7 @@ def main():
                 else:
                     eng.submit_prepared_host(b)
                 if args.e2e_mode != "h2d":
-                    eng.read_pictures_async(sids, [dst[i]] * S, out_ptrs[i % nbuf])
+                    eng.read_pictures_async(sids, dst[i], out_ptrs[i % nbuf])
 
         e2e_step()
         eng.sync()
@@ -328,7 +346,7 @@ def main():
         last = (npic - 1) % nbuf
         from h264_video_decoder_demo_b200 import abi
         for s in ((0, S - 1) if args.e2e_mode != "h2d" else ()):
-            if abi.checksum(out_host[last][s * eng.frame_bytes:(s + 1) * eng.frame_bytes].tobytes()) != rp.pictures[-1].sum_post:
+            if abi.checksum(out_host[last][s * eng.frame_bytes:(s + 1) * eng.frame_bytes].tobytes()) != want[-1][s]:
                 raise SystemExit("PARITY FAILURE in the e2e path")
         sharding.barrier()
         eng.timer_start()
@@ -340,7 +358,8 @@ def main():
         e2e_dev_ms = eng.timer_stop()
         e2e_kt = eng.kernel_times()
         e2e = {"value": round(S * npic * args.e2e_steps * world / t1, 1), "unit": UNIT,
-               "h2d_bytes_per_step": int(sum(p.nbytes() for p in rp.pictures) * S), "d2h_bytes_per_step": int(npic * S * eng.frame_bytes),
+               "h2d_bytes_per_step": int(sum(variants[var_of[s]]["rp"].pictures[pic_of(s, i)].nbytes() for s in sids for i in range(npic))),
+               "d2h_bytes_per_step": int(npic * S * eng.frame_bytes),
                "steps": args.e2e_steps, "device_ms_per_step": round(e2e_dev_ms / args.e2e_steps, 1),
                "kernel_ms_per_step": {k: round(v["ms"] / args.e2e_steps, 1) for k, v in e2e_kt.items()}, "timing": "host wall clock around submit+read-back of every picture, synchronised on both sides, max over ranks"}
 
@@ -359,9 +378,11 @@ def main():
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "bundled reference bitstream pre-parsed by the reference's own parser (SoA resident in HBM)",
-            "config": {"workload": f"{stem}.h264 x {S} concurrent replicas per GPU" + ("" if is_full else " (golden prefix only: full replay not built)"),
+            "config": {"workload": (f"{stem}.h264 x {S} concurrent replicas per GPU" if len(stems) == 1 else
+                                    f"all {len(stems)} bundled streams ({', '.join(stems)}) dealt round-robin over {S} concurrent streams per GPU")
+                                   + ("" if is_full else " (golden prefix only: full replay not built)"),
                        "pictures_per_step_per_gpu": S * npic, "streams_per_gpu": S, "picture": "1920x1088 I420",
-                       "l2": "inputs larger than L2: one distinct SoA copy + 17-surface DPB per replica (%.1f GB per GPU)" % ((sum(rs[0].blob_bytes) + 17 * eng.frame_bytes) * S / 1e9),
+                       "l2": "inputs larger than L2: one distinct SoA copy + 17-surface DPB per stream (%.1f GB per GPU)" % ((sum(sum(r.blob_bytes) for r in rs) + 17 * eng.frame_bytes * S) / 1e9),
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }) + "\n").encode())

@@ -267,7 +267,16 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_deblock(const
             rs_wait(rs, min(x + 2, wmb), x, lane);
             for (int s = 0; s < per; s++) {
                 const int a = (row * wmb + x) * per + s;
-                if (a < P.deblock_stop && anyflag[a]) deblock_mb(P, a, lane);
+                if (a < P.deblock_stop && anyflag[a]) {
+                    // frame MB whose left and above pairs are frame pairs: staged filter; else the literal DB:639 walk
+                    const H264B2MbInfo I = P.info[a];
+                    const DbCtx c = db_ctx(P, a, I);
+                    const int w = P.wmb, pr = a >> 1;
+                    bool tile = P.mbaff && !(I.flags & H264B2_MBF_FIELD) && !c.leftflag && !c.dbltop;
+                    if (tile && pr % w > 0) tile = !(P.info[a - 2].flags & H264B2_MBF_FIELD);
+                    if (tile && pr >= w) tile = !(P.info[2 * (pr - w)].flags & H264B2_MBF_FIELD);
+                    if (tile) deblock_mb_tile(P, a, c.A, c.B, lane, tiles[warp]); else deblock_mb(P, a, lane);
+                }
             }
             rs_publish(rs, x + 1, lane);
         }

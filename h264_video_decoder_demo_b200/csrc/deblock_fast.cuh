@@ -54,6 +54,42 @@ __device__ __forceinline__ void filter_words(uint32_t &Pw, uint32_t &Qw, int bS,
     Qw = (uint32_t)nq0 | ((uint32_t)nq1 << 8) | ((uint32_t)nq2 << 16) | ((uint32_t)q3 << 24);
 }
 
+// vertical phase on the staged tile: lane = sample row; step i filters the edge between tile words i and i+1
+__device__ __forceinline__ void db_vertical(DbTile &T, int comp, int k, uint32_t v, const DbThr &tA, const DbThr &tI) {
+    uint32_t *rowp = comp ? &T.C[comp - 1][4 + k][0] : &T.L[4 + k][0];
+    if (v) {
+        uint32_t w0 = rowp[0], w1 = rowp[1], w2 = rowp[2], w3 = 0, w4 = 0;
+        if (!comp) { w3 = rowp[3]; w4 = rowp[4]; }
+        if (v & 0xF) filter_words(w0, w1, v & 15, tA, comp);
+        if (v & 0xF0) filter_words(w1, w2, (v >> 4) & 15, tI, comp);
+        if (v & 0xF00) filter_words(w2, w3, (v >> 8) & 15, tI, comp);
+        if (v & 0xF000) filter_words(w3, w4, (v >> 12) & 15, tI, comp);
+        rowp[0] = w0; rowp[1] = w1; rowp[2] = w2;
+        if (!comp) { rowp[3] = w3; rowp[4] = w4; }
+    }
+}
+// horizontal phase: lane = sample column; the column is gathered into words of 4 rows, then the same 4 steps
+__device__ __forceinline__ void db_horizontal(DbTile &T, int comp, int k, uint32_t h, const DbThr &tB, const DbThr &tI) {
+    if (h) {
+        uint8_t *col = comp ? (uint8_t *)&T.C[comp - 1][0][0] + 4 + k : (uint8_t *)&T.L[0][0] + 4 + k;
+        const int sb = comp ? 12 : 20;
+        uint32_t cw[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            if (j < 3 || !comp) cw[j] = (uint32_t)col[(4 * j) * sb] | ((uint32_t)col[(4 * j + 1) * sb] << 8) | ((uint32_t)col[(4 * j + 2) * sb] << 16) | ((uint32_t)col[(4 * j + 3) * sb] << 24);
+            else cw[j] = 0;
+        }
+        if (h & 0xF) filter_words(cw[0], cw[1], h & 15, tB, comp);
+        if (h & 0xF0) filter_words(cw[1], cw[2], (h >> 4) & 15, tI, comp);
+        if (h & 0xF00) filter_words(cw[2], cw[3], (h >> 8) & 15, tI, comp);
+        if (h & 0xF000) filter_words(cw[3], cw[4], (h >> 12) & 15, tI, comp);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            if (j < 3 || !comp) { col[(4 * j) * sb] = (uint8_t)cw[j]; col[(4 * j + 1) * sb] = (uint8_t)(cw[j] >> 8); col[(4 * j + 2) * sb] = (uint8_t)(cw[j] >> 16); col[(4 * j + 3) * sb] = (uint8_t)(cw[j] >> 24); }
+        }
+    }
+}
+
 __device__ __forceinline__ int db_next_work(const uint32_t *work, int x, int wmb) {   // first work MB with index > x, or wmb
     for (int i = x + 1; i < wmb; ) {
         const uint32_t w = work[i >> 5] >> (i & 31);
@@ -142,43 +178,14 @@ __device__ inline void deblock_row_fast(const PicDev &P, int row, int lane, DbTi
         const bool early = topf && rs_try(rs, min(x + 2, wmb), lane);
         if (early && toprow) topw = __ldcg((const uint32_t *)toprow);
         __syncwarp();
-        uint32_t *rowp = comp ? &T.C[comp - 1][4 + k][0] : &T.L[4 + k][0];
-        // ---- vertical edges: lane = sample row; step i filters the edge between tile words i and i+1
-        if (v) {
-            uint32_t w0 = rowp[0], w1 = rowp[1], w2 = rowp[2], w3 = 0, w4 = 0;
-            if (!comp) { w3 = rowp[3]; w4 = rowp[4]; }
-            if (v & 0xF) filter_words(w0, w1, v & 15, tA, comp);
-            if (v & 0xF0) filter_words(w1, w2, (v >> 4) & 15, tI, comp);
-            if (v & 0xF00) filter_words(w2, w3, (v >> 8) & 15, tI, comp);
-            if (v & 0xF000) filter_words(w3, w4, (v >> 12) & 15, tI, comp);
-            rowp[0] = w0; rowp[1] = w1; rowp[2] = w2;
-            if (!comp) { rowp[3] = w3; rowp[4] = w4; }
-        }
+        db_vertical(T, comp, k, v, tA, tI);
         if (topf) {
             if (!early) { rs_wait(rs, min(x + 2, wmb), x, lane); if (toprow) topw = __ldcg((const uint32_t *)toprow); }
             if (lane < 16) T.L[lane >> 2][1 + (lane & 3)] = topw;
             else if (lane < 24) { const int l = lane - 16; T.C[l >> 2][2 + ((l >> 1) & 1)][1 + (l & 1)] = topw; }
         }
         __syncwarp();
-        // ---- horizontal edges: lane = sample column; gather the column into words of 4 rows, same 4 steps
-        if (h) {
-            uint8_t *col = comp ? (uint8_t *)&T.C[comp - 1][0][0] + 4 + k : (uint8_t *)&T.L[0][0] + 4 + k;
-            const int sb = comp ? 12 : 20;
-            uint32_t cw[5];
-#pragma unroll
-            for (int j = 0; j < 5; j++) {
-                if (j < 3 || !comp) cw[j] = (uint32_t)col[(4 * j) * sb] | ((uint32_t)col[(4 * j + 1) * sb] << 8) | ((uint32_t)col[(4 * j + 2) * sb] << 16) | ((uint32_t)col[(4 * j + 3) * sb] << 24);
-                else cw[j] = 0;
-            }
-            if (h & 0xF) filter_words(cw[0], cw[1], h & 15, tB, comp);
-            if (h & 0xF0) filter_words(cw[1], cw[2], (h >> 4) & 15, tI, comp);
-            if (h & 0xF00) filter_words(cw[2], cw[3], (h >> 8) & 15, tI, comp);
-            if (h & 0xF000) filter_words(cw[3], cw[4], (h >> 12) & 15, tI, comp);
-#pragma unroll
-            for (int j = 0; j < 5; j++) {
-                if (j < 3 || !comp) { col[(4 * j) * sb] = (uint8_t)cw[j]; col[(4 * j + 1) * sb] = (uint8_t)(cw[j] >> 8); col[(4 * j + 2) * sb] = (uint8_t)(cw[j] >> 16); col[(4 * j + 3) * sb] = (uint8_t)(cw[j] >> 24); }
-            }
-        }
+        db_horizontal(T, comp, k, h, tB, tI);
         __syncwarp();
         // ---- write back: columns -4..11 of the MB's rows (the left MB's last columns are final now), the
         //      rows above if they were filtered, and at the end of the row also columns 12..15
@@ -211,4 +218,71 @@ __device__ inline void deblock_row_fast(const PicDev &P, int row, int lane, DbTi
         x = xn;
     }
     rs_publish(rs, wmb, lane);
+}
+
+// One frame macroblock of an MBAFF picture whose left and above neighbour pairs are frame pairs too (no mixed edges,
+// no field stepping): same staged filter, but every sample comes from / goes to global memory for this MB alone (the
+// pair-interleaved address order rules out the row-wise carry).  v/h: per-line strengths written by k_bs for MBAFF
+// pictures; A/B: left / top neighbour MB for the thresholds (-1 = unavailable -> the MB itself, Q14).
+__device__ inline void deblock_mb_tile(const PicDev &P, int a, int A, int B, int lane, DbTile &T) {
+    const int W = P.wmb * 16, H = P.hmb * 16, Wc = W >> 1;
+    const int comp = lane < 16 ? 0 : lane < 24 ? 1 : 2;
+    const int k = comp ? (lane & 7) : lane;
+    int x0, y0;
+    mb_origin(P, a, 0, x0, y0);
+    const uint32_t v = P.bs[(size_t)a * 64 + lane], hraw = P.bs[(size_t)a * 64 + 32 + lane];
+    const uint32_t h = (hraw & 0xF) | (((hraw >> 8) & 0xFFF) << 4);       // slots (0, 2, 3, 4) -> steps (0, 1, 2, 3)
+    const H264B2MbInfo I = P.info[a];
+    int qq = I.mb_class == H264B2_MB_IPCM ? 0 : I.qpy, qa = qq, qb = qq;
+    if (A >= 0) { const H264B2MbInfo IA = P.info[A]; qa = IA.mb_class == H264B2_MB_IPCM ? 0 : IA.qpy; }
+    if (B >= 0) { const H264B2MbInfo IB = P.info[B]; qb = IB.mb_class == H264B2_MB_IPCM ? 0 : IB.qpy; }
+    if (comp) { qq = chroma_qp(P, qq, comp - 1); qa = chroma_qp(P, qa, comp - 1); qb = chroma_qp(P, qb, comp - 1); }
+    DbThr tA, tB, tI;
+    {
+        const int oa = I.filter_offset_a, ob = I.filter_offset_b;
+        const int q3[3] = { qa, qb, qq };
+        DbThr *t3[3] = { &tA, &tB, &tI };
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int qpav = (q3[i] + qq + 1) >> 1;
+            t3[i]->ia = clip3i(0, 51, qpav + oa);
+            t3[i]->alpha = g_alpha_tab[t3[i]->ia]; t3[i]->beta = g_beta_tab[clip3i(0, 51, qpav + ob)];
+        }
+    }
+    const int topf = __any_sync(0xffffffffu, (h & 15u) != 0);
+    uint8_t *Y = P.dst + (size_t)y0 * W + x0;
+    uint8_t *Cbase = P.dst + (size_t)W * H;
+    const size_t cplane = (size_t)Wc * (H >> 1);
+    const int yc = y0 >> 1, xc = x0 >> 1;
+    // stage: own samples, left columns, rows above
+#pragma unroll
+    for (int t = 0; t < 2; t++) { const int w = lane + 32 * t; T.L[4 + (w >> 2)][1 + (w & 3)] = __ldcg((const uint32_t *)(Y + (size_t)(w >> 2) * W + (w & 3) * 4)); }
+    { const int c = lane >> 4, cl = lane & 15; T.C[c][4 + (cl >> 1)][1 + (cl & 1)] = __ldcg((const uint32_t *)(Cbase + c * cplane + (size_t)(yc + (cl >> 1)) * Wc + xc + (cl & 1) * 4)); }
+    if (x0 > 0) {
+        if (lane < 16) T.L[4 + lane][0] = __ldcg((const uint32_t *)(Y + (size_t)lane * W - 4));
+        else { const int l = lane - 16, c = l >> 3, r = l & 7; T.C[c][4 + r][0] = __ldcg((const uint32_t *)(Cbase + c * cplane + (size_t)(yc + r) * Wc + xc - 4)); }
+    }
+    if (topf) {
+        if (lane < 16) T.L[lane >> 2][1 + (lane & 3)] = __ldcg((const uint32_t *)(Y - (size_t)(4 - (lane >> 2)) * W + (lane & 3) * 4));
+        else if (lane < 24) { const int l = lane - 16, c = l >> 2, r = (l >> 1) & 1, w = l & 1;
+            T.C[c][2 + r][1 + w] = __ldcg((const uint32_t *)(Cbase + c * cplane + (size_t)(yc - 2 + r) * Wc + xc + w * 4)); }
+    }
+    __syncwarp();
+    db_vertical(T, comp, k, v, tA, tI);
+    __syncwarp();
+    db_horizontal(T, comp, k, h, tB, tI);
+    __syncwarp();
+    // write back everything this MB may have changed
+#pragma unroll
+    for (int t = 0; t < 2; t++) { const int w = lane + 32 * t; *(uint32_t *)(Y + (size_t)(w >> 2) * W + (w & 3) * 4) = T.L[4 + (w >> 2)][1 + (w & 3)]; }
+    { const int c = lane >> 4, cl = lane & 15; *(uint32_t *)(Cbase + c * cplane + (size_t)(yc + (cl >> 1)) * Wc + xc + (cl & 1) * 4) = T.C[c][4 + (cl >> 1)][1 + (cl & 1)]; }
+    if (x0 > 0) {
+        if (lane < 16) *(uint32_t *)(Y + (size_t)lane * W - 4) = T.L[4 + lane][0];
+        else { const int l = lane - 16, c = l >> 3, r = l & 7; *(uint32_t *)(Cbase + c * cplane + (size_t)(yc + r) * Wc + xc - 4) = T.C[c][4 + r][0]; }
+    }
+    if (topf) {
+        if (lane < 12) { const int rr = 1 + lane / 4, jj = lane & 3; *(uint32_t *)(Y + (size_t)(rr - 4) * W + jj * 4) = T.L[rr][1 + jj]; }
+        else if (lane >= 16 && lane < 20) { const int l = lane - 16, cc = l >> 1, jj = l & 1; *(uint32_t *)(Cbase + cc * cplane + (size_t)(yc - 1) * Wc + xc + jj * 4) = T.C[cc][3][1 + jj]; }
+    }
+    __syncwarp();
 }

@@ -177,8 +177,12 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     int avA = 0, avB = 0, avC = 0, avD = 0;
     if (FAST) {
         // availability of the four neighbouring MBs (PB:2887-2947) incl. constrained_intra_pred (PB:1129)
-        const int w = P.wmb, mx = a % w;
-        const int nA = mx > 0 ? a - 1 : -1, nB = a - w, nC = (mx + 1 < w) ? a - w + 1 : -1, nD = mx > 0 ? a - w - 1 : -1;
+        // geometric neighbours; under MBAFF (frame MBs among frame pairs only, see intra_fast_ok) the address of the
+        // MB at (x, y) is 2*((y/2)*w + x) + y%2, and "address <= current" makes C unavailable for bottom MBs (PB:3058-3077)
+        const int w = P.wmb, mx = x0 >> 4, my = y0 >> 4;
+        auto addr = [&](int x, int y) { return P.mbaff ? 2 * ((y >> 1) * w + x) + (y & 1) : y * w + x; };
+        const int nA = mx > 0 ? addr(mx - 1, my) : -1, nB = my > 0 ? addr(mx, my - 1) : -1;
+        const int nC = (my > 0 && mx + 1 < w) ? addr(mx + 1, my - 1) : -1, nD = (mx > 0 && my > 0) ? addr(mx - 1, my - 1) : -1;
         avA = nA >= 0 && avail_addr(P, a, nA) && !(P.info[nA].flags & H264B2_MBF_CIP_UNAVAIL);
         avB = nB >= 0 && avail_addr(P, a, nB) && !(P.info[nB].flags & H264B2_MBF_CIP_UNAVAIL);
         avC = nC >= 0 && avail_addr(P, a, nC) && !(P.info[nC].flags & H264B2_MBF_CIP_UNAVAIL);
@@ -371,6 +375,23 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     }
 }
 
+// May macroblock `a` of an MBAFF picture take the staged (geometric) path?  Yes when it is a frame MB and every pair
+// it can take neighbour samples from (left, above-left, above, above-right) is a frame pair too: then 6.4.12.2
+// degenerates to the geometric neighbours of a progressive picture.
+__device__ __forceinline__ bool intra_fast_ok(const PicDev &P, int a) {
+    if (!P.mbaff) return true;
+    if (P.info[a].flags & H264B2_MBF_FIELD) return false;
+    const int w = P.wmb, pr = a >> 1, px = pr % w, py = pr / w;
+    bool ok = true;
+    if (px > 0) ok &= !(P.info[2 * (pr - 1)].flags & H264B2_MBF_FIELD);
+    if (py > 0) {
+        ok &= !(P.info[2 * (pr - w)].flags & H264B2_MBF_FIELD);
+        if (px > 0) ok &= !(P.info[2 * (pr - w - 1)].flags & H264B2_MBF_FIELD);
+        if (px + 1 < w) ok &= !(P.info[2 * (pr - w + 1)].flags & H264B2_MBF_FIELD);
+    }
+    return ok;
+}
+
 // Wavefront driver (see wavefront.cuh): one CTA per band of WF_ROWS MB rows, one warp per row.
 __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ IntraWarpSmem sm[WF_ROWS];
@@ -426,7 +447,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
                 const int a = (row * wmb + x) * per + s;
                 const H264B2MbInfo I = P.info[a];
                 if (I.mb_class >= H264B2_MB_I4x4 && I.mb_class <= H264B2_MB_IPCM) {
-                    if (P.mbaff) intra_mb<false>(P, a, I, lane, sm[warp]); else intra_mb<true>(P, a, I, lane, sm[warp]);
+                    if (intra_fast_ok(P, a)) intra_mb<true>(P, a, I, lane, sm[warp]); else intra_mb<false>(P, a, I, lane, sm[warp]);
                 }
             }
             rs_publish(rs, x + 1, lane);

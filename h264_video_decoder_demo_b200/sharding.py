@@ -61,3 +61,17 @@ def barrier():
     d = _dist()
     if d is not None and d.get_world_size() > 1:
         d.barrier()
+
+
+def closed_gop_starts(rp) -> List[int]:
+    """Decode indices at which a closed GOP starts (an IDR picture: the DPB is wiped, RPL:1506-1518, the output
+    queue is flushed, VD:389-414, POC restarts, RPL:49-53), so that [start_k, start_k+1) can be reconstructed
+    independently of everything before it.  The replay container does not carry nal_unit_type; an IDR is
+    recognised as an I picture whose PicOrderCnt is 0 and which no later picture precedes in output order."""
+    starts = []
+    for i, p in enumerate(rp.pictures):
+        if p.slice_type % 5 == 2 and p.poc == 0 and p.has_inter == 0:
+            starts.append(i)
+    if not starts or starts[0] != 0:
+        starts.insert(0, 0)
+    return starts

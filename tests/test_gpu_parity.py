@@ -191,3 +191,26 @@ def test_error_behaviour():
     with pytest.raises(engine.EngineError):
         eng.submit([0], [p])
     eng.close()
+
+
+def test_closed_gops_of_one_stream_decode_in_parallel():
+    """closed GOPs shard like independent streams.  The two GOPs of a HeavyHand stream (IDRs at pictures
+    0 and 46) are reconstructed CONCURRENTLY on two DPBs of one context; every picture still equals the reference's
+    full-stream decode (the GOP-0 tail picture is deblocked there, and so it is here)."""
+    from h264_video_decoder_demo_b200 import sharding
+    files = [f for f in full_files() if "B_frames.cabac" in f]
+    if not files:
+        pytest.skip("full replays not built")
+    rp = replay.load_replay(files[0])
+    starts = sharding.closed_gop_starts(rp)
+    assert starts == [0, 46]
+    bounds = starts + [len(rp.pictures)]
+    eng = engine.Engine(0, len(starts), rp.width_mbs, rp.height_mbs)
+    rs = engine.ResidentStream(eng, rp)
+    depth = max(bounds[g + 1] - bounds[g] for g in range(len(starts)))
+    for k in range(depth):
+        sids = [g for g in range(len(starts)) if bounds[g] + k < bounds[g + 1]]
+        idx = [bounds[g] + k for g in sids]
+        eng.submit_device(sids, [rs.params[i] for i in idx])
+        assert eng.checksums(sids, [rp.pictures[i].dst_surface for i in idx]) == [rp.pictures[i].sum_post for i in idx], f"step {k}"
+    eng.close()
