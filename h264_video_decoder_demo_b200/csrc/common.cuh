@@ -25,7 +25,8 @@ struct alignas(16) PicDev {
     unsigned long long    frame_bytes;
     int wmb, hmb, mbaff, cqp0, cqp1;
     int deblock_enable, deblock_stop;
-    int n_weights, reserved;
+    int n_weights;
+    int generic;                       // 1: MBAFF picture (or wider than 256 MBs): literal per-sample-line paths; 0: progressive fast paths
     int pad_[2];                       // sizeof(PicDev) is a multiple of 16: the batch prologue copies it as uint4
 };
 static_assert(sizeof(PicDev) % 16 == 0, "PicDev must be a multiple of 16 bytes");

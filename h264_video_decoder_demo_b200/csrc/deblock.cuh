@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) k_bs(const PicDev *pics) {
     if (a >= nmb || !P.deblock_enable || a >= P.deblock_stop) return;
     const H264B2MbInfo I = P.info[a];
     const DbCtx c = db_ctx(P, a, I);
-    if (!P.mbaff) {
+    if (!P.generic) {
         // ---- compact record for progressive pictures (consumed by deblock_row_fast): without MBAFF the strength
         // is constant over each 4-sample segment and chroma line k reuses luma line 2k (DB:871-880), so 16 vertical
         // + 16 horizontal values describe the MB.  16 words per MB at bs[a*16]:
@@ -237,6 +237,9 @@ __device__ inline void deblock_mb(const PicDev &P, int a, int lane) {
 
 #include "deblock_fast.cuh"
 
+// GENERIC = false: every picture of the launch is progressive (PicDev::generic == 0) -> only the staged fast path is
+// compiled in (smaller code, fewer registers); GENERIC = true: MBAFF pictures, literal per-sample-line walk.
+template <bool GENERIC>
 __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_deblock(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ DbTile tiles[WF_ROWS];
     __shared__ int s_prog[WF_ROWS];
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_deblock(const
     const int rows = P.hmb / per, wmb = P.wmb, nmb = P.wmb * P.hmb;
     if (row >= rows) return;
     RowSync rs = rs_init(s_prog, warp, row, rows, P.progress + P.hmb, wmb);     // progress[1][row]
-    if (!P.mbaff && wmb <= 256) { deblock_row_fast(P, row, lane, tiles[warp], rs); return; }
+    if (!GENERIC) { deblock_row_fast(P, row, lane, tiles[warp], rs); return; }
     const uint32_t *anyflag = P.bs + (size_t)nmb * 64;
     for (int xb = 0; xb < wmb; xb += 32) {
         const int xl = xb + lane;

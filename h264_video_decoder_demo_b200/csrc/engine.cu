@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include <new>
 
 #include "h264_recon_b200.h"
@@ -76,8 +77,8 @@ struct H264B2Context {
     // joined back into `st`: the latency-bound wavefront kernels of one group overlap the issue-bound kernels
     // (and the wavefronts) of the others.
     int groups, group_min;
-    cudaStream_t st_g[MAX_GROUPS];
-    cudaEvent_t fork_ev, join_ev[MAX_GROUPS];
+    cudaStream_t st_g[MAX_GROUPS], st_side[MAX_GROUPS];
+    cudaEvent_t fork_ev, join_ev[MAX_GROUPS], side_fork[MAX_GROUPS], side_join[MAX_GROUPS];
     // descriptor ring
     PicDev *h_desc, *h_desc_dev, *d_desc;     // h_desc: mapped pinned host memory, h_desc_dev: its device alias
     cudaEvent_t desc_ev[DESC_RING];
@@ -192,7 +193,7 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaMemset(c->surfaces, 0, total + (size_t)width_mbs * 64));
     CK(cudaMalloc(&c->bs, (size_t)n_streams * c->nmb * 65 * 4));
     CK(cudaMalloc(&c->res, (size_t)n_streams * c->nmb * RES_MB_STRIDE * 2));
-    c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 2 * MAX_GROUPS;
+    c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 4 * MAX_GROUPS;
     {
         const char *g = getenv("H264B2_GROUPS"), *gm = getenv("H264B2_GROUP_MIN");
         c->groups = g ? atoi(g) : 1;      // measured (S=128): 1 group 15.0k, 2 groups 14.0k, 4 groups 13.3k frames/s — the GPU is already issue-bound
@@ -205,7 +206,11 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < MAX_GROUPS; i++) { CK(cudaStreamCreateWithFlags(&c->st_g[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming)); }
+    for (int i = 0; i < MAX_GROUPS; i++) {
+        CK(cudaStreamCreateWithFlags(&c->st_g[i], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->side_fork[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->side_join[i], cudaEventDisableTiming));
+    }
     CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     CK(cudaHostAlloc(&c->h_desc, sizeof(PicDev) * n_streams * DESC_RING, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void **)&c->h_desc_dev, c->h_desc, 0));
@@ -243,7 +248,7 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     free(c->ev);
     cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
     cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_d2h);
-    for (int i = 0; i < MAX_GROUPS; i++) { cudaStreamDestroy(c->st_g[i]); cudaEventDestroy(c->join_ev[i]); }
+    for (int i = 0; i < MAX_GROUPS; i++) { cudaStreamDestroy(c->st_g[i]); cudaStreamDestroy(c->st_side[i]); cudaEventDestroy(c->join_ev[i]); cudaEventDestroy(c->side_fork[i]); cudaEventDestroy(c->side_join[i]); }
     cudaEventDestroy(c->fork_ev);
     delete c;
     return 0;
@@ -288,9 +293,16 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
     CK(cudaEventSynchronize(c->desc_ev[ring]));
     PicDev *hd = c->h_desc + (size_t)ring * c->n_streams, *dd = c->d_desc + (size_t)ring * c->n_streams;
     int any_inter = 0, any_deblock = 0;
-    for (int i = 0; i < n; i++) {
+    // descriptors are laid out progressive pictures first, then "generic" ones (MBAFF, or wider than the fast paths
+    // support): the wavefront kernels are launched once per kind, each with only its own code path compiled in
+    std::vector<int> order; order.reserve(n);
+    for (int pass = 0; pass < 2; pass++)
+        for (int i = 0; i < n; i++) { const int gen = pics[i].mbaff_frame_flag || c->wmb > 256; if (gen == pass) order.push_back(i); }
+    int n_prog = 0;
+    for (int j = 0; j < n; j++) {
+        const int i = order[j];
         const H264B2PicParams &p = pics[i];
-        PicDev &d = hd[i];
+        PicDev &d = hd[j];
         d.info = p.mb_info; d.modes = p.intra_modes; d.coef_off = p.coef_offset; d.motion = p.has_inter ? p.motion : nullptr;
         d.weights = p.weights; d.coefs = p.coefs;
         d.ls4 = p.custom_scaling ? p.level_scale4 : c->ls_flat;
@@ -303,14 +315,16 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.frame_bytes = c->frame_bytes;
         d.wmb = c->wmb; d.hmb = c->hmb; d.mbaff = p.mbaff_frame_flag; d.cqp0 = p.chroma_qp_offset[0]; d.cqp1 = p.chroma_qp_offset[1];
         d.deblock_enable = p.deblock_enable; d.deblock_stop = p.deblock_stop_mb < c->nmb ? p.deblock_stop_mb : c->nmb;
-        d.n_weights = p.n_weights; d.reserved = 0;
+        d.n_weights = p.n_weights;
+        d.generic = p.mbaff_frame_flag || c->wmb > 256;
+        n_prog += !d.generic;
         any_inter |= p.has_inter; any_deblock |= p.deblock_enable;
     }
-    int *tickets = c->progress + (c->progress_ints - DESC_RING * 2 * MAX_GROUPS) + ring * 2 * MAX_GROUPS;
+    int *tickets = c->progress + (c->progress_ints - DESC_RING * 4 * MAX_GROUPS) + ring * 4 * MAX_GROUPS;
     class_begin(c, 0, c->st);
     k_prologue<<<1, 256, 0, c->st>>>((const uint4 *)(c->h_desc_dev + (size_t)ring * c->n_streams), (uint4 *)dd, (int)(sizeof(PicDev) * n / 16), c->progress, (int)c->progress_ints);
     CK(cudaEventRecord(c->desc_ev[ring], c->st));
-    for (int i = 0; i < n; i++) if (pics[i].clear_surface) CK(cudaMemsetAsync(hd[i].dst, 0, c->frame_bytes, c->st));
+    for (int j = 0; j < n; j++) if (pics[order[j]].clear_surface) CK(cudaMemsetAsync(hd[j].dst, 0, c->frame_bytes, c->st));
     class_end(c, 0, c->st);
     int G = c->groups;
     while (G > 1 && n / G < c->group_min) G--;
@@ -322,7 +336,8 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         cudaStream_t sg = G > 1 ? c->st_g[g] : c->st;
         if (G > 1) CK(cudaStreamWaitEvent(sg, c->fork_ev, 0));
         int g_inter = 0, g_deblock = 0;
-        for (int i = b0; i < b1; i++) { g_inter |= pics[i].has_inter; g_deblock |= pics[i].deblock_enable; }
+        for (int j = b0; j < b1; j++) { g_inter |= pics[order[j]].has_inter; g_deblock |= pics[order[j]].deblock_enable; }
+        const int np = std::max(0, std::min(b1, n_prog) - b0), nq = ng - np;      // progressive / generic pictures of this group
         const PicDev *dg = dd + b0;
         class_begin(c, 5, sg);
         k_residual<<<dim3((c->nmb + 7) / 8, ng), 256, 0, sg>>>(dg);
@@ -332,16 +347,39 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
             k_inter<<<dim3((c->nmb + 7) / 8, ng), 128, 0, sg>>>(dg);
             class_end(c, 1, sg);
         }
-        class_begin(c, 2, sg);
-        k_intra<<<ng * bands, WF_THREADS, 0, sg>>>(dg, ng, bands, tickets + 2 * g);
-        class_end(c, 2, sg);
+        // boundary strengths need only side info, not samples: compute them before the wavefronts so that the
+        // intra -> deblock chains of the progressive and of the generic (MBAFF) pictures can run side by side
         if (g_deblock) {
             class_begin(c, 3, sg);
             k_bs<<<dim3((c->nmb + 7) / 8, ng), 256, 0, sg>>>(dg);
             class_end(c, 3, sg);
-            class_begin(c, 4, sg);
-            k_deblock<<<ng * bands, WF_THREADS, 0, sg>>>(dg, ng, bands, tickets + 2 * g + 1);
-            class_end(c, 4, sg);
+        }
+        cudaStream_t sq = sg;
+        if (np && nq) {                 // generic pictures continue on a side stream
+            sq = c->st_side[g];
+            CK(cudaEventRecord(c->side_fork[g], sg));
+            CK(cudaStreamWaitEvent(sq, c->side_fork[g], 0));
+        }
+        if (np) {
+            class_begin(c, 2, sg);
+            k_intra<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g);
+            class_end(c, 2, sg);
+            if (g_deblock) {
+                class_begin(c, 4, sg);
+                k_deblock<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g + 2);
+                class_end(c, 4, sg);
+            }
+        }
+        if (nq) {
+            class_begin(c, 2, sq);
+            k_intra<true><<<nq * bands, WF_THREADS, 0, sq>>>(dg + np, nq, bands, tickets + 4 * g + 1);
+            class_end(c, 2, sq);
+            if (g_deblock) {
+                class_begin(c, 4, sq);
+                k_deblock<true><<<nq * bands, WF_THREADS, 0, sq>>>(dg + np, nq, bands, tickets + 4 * g + 3);
+                class_end(c, 4, sq);
+            }
+            if (sq != sg) { CK(cudaEventRecord(c->side_join[g], sq)); CK(cudaStreamWaitEvent(sg, c->side_join[g], 0)); }
         }
         if (G > 1) { CK(cudaEventRecord(c->join_ev[g], sg)); CK(cudaStreamWaitEvent(c->st, c->join_ev[g], 0)); }
     }

@@ -212,7 +212,7 @@ __device__ __forceinline__ int weigh(const H264B2Weight &w, int c, int have0, in
 // grid: (ceil(n_mbs / 8), n_pics); block: 128 threads = 4 warps; warp w = 4x4-block row `by` of 8 consecutive
 // macroblock addresses, lane = (mb_in_group << 2) | bx.
 #ifndef INTER_MIN_BLOCKS
-#define INTER_MIN_BLOCKS 6
+#define INTER_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *pics) {
     const PicDev &P = pics[blockIdx.y];
@@ -230,26 +230,33 @@ __global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *p
     const H264B2MbMotion &M = P.motion[a];
     const int r = by4 * 4 + bx4, bx = bx4 * 4, by = by4 * 4, q = (by4 >> 1) * 2 + (bx4 >> 1);
 
+    // Both lists run through ONE copy of the interpolation code (the loop is deliberately not unrolled: the kernel
+    // was instruction-cache bound, ncu stall_no_instruction was its top stall reason at 80 KB of SASS).
     uint32_t pl[2][4];
     int pc[2][2][4];
     int have[2];
 #pragma unroll
+    for (int i = 0; i < 4; i++) { pl[0][i] = pl[1][i] = 0; pc[0][0][i] = pc[0][1][i] = pc[1][0][i] = pc[1][1][i] = 0; }
+    have[0] = M.ref_surf[0][q] >= 0; have[1] = M.ref_surf[1][q] >= 0;
+#pragma unroll 1
     for (int l = 0; l < 2; l++) {
         const int code = M.ref_surf[l][q];
-        have[l] = code >= 0;
-        if (have[l]) {
-            RefViewDev rv;
-            ref_view(P, code, rv);
-            const int mvx = M.mv[l][r][0], mvy = M.mv[l][r][1];
-            int mvcy = mvy;
-            if (field) { if (rv.view == 1 && (a & 1)) mvcy += 2; else if (rv.view == 2 && !(a & 1)) mvcy -= 2; }   // IP:2019-2043
-            luma_block_pred(rv.base[0], rv.stride[0], rv.wclamp[0], rv.hclamp[0], W, x0 + bx + (mvx >> 2), yA + by + (mvy >> 2), mvx & 3, mvy & 3, pl[l]);
-            const int xC = (x0 + bx) / 2 + (mvx >> 3), yC = (yA + by) / 2 + (mvcy >> 3);
-            chroma_block_pred(rv.base[1], rv.stride[1], rv.wclamp[1], rv.hclamp[1], Wc, xC, yC, mvx & 7, mvcy & 7, pc[l][0]);
-            chroma_block_pred(rv.base[2], rv.stride[2], rv.wclamp[2], rv.hclamp[2], Wc, xC, yC, mvx & 7, mvcy & 7, pc[l][1]);
-        } else {
+        if (code < 0) continue;
+        RefViewDev rv;
+        ref_view(P, code, rv);
+        const int mvx = M.mv[l][r][0], mvy = M.mv[l][r][1];
+        int mvcy = mvy;
+        if (field) { if (rv.view == 1 && (a & 1)) mvcy += 2; else if (rv.view == 2 && !(a & 1)) mvcy -= 2; }   // IP:2019-2043
+        uint32_t tl[4];
+        int tc0[4], tc1[4];
+        luma_block_pred(rv.base[0], rv.stride[0], rv.wclamp[0], rv.hclamp[0], W, x0 + bx + (mvx >> 2), yA + by + (mvy >> 2), mvx & 3, mvy & 3, tl);
+        const int xC = (x0 + bx) / 2 + (mvx >> 3), yC = (yA + by) / 2 + (mvcy >> 3);
+        chroma_block_pred(rv.base[1], rv.stride[1], rv.wclamp[1], rv.hclamp[1], Wc, xC, yC, mvx & 7, mvcy & 7, tc0);
+        chroma_block_pred(rv.base[2], rv.stride[2], rv.wclamp[2], rv.hclamp[2], Wc, xC, yC, mvx & 7, mvcy & 7, tc1);
 #pragma unroll
-            for (int i = 0; i < 4; i++) { pl[l][i] = 0; pc[l][0][i] = 0; pc[l][1][i] = 0; }
+        for (int i = 0; i < 4; i++) {
+            if (l == 0) { pl[0][i] = tl[i]; pc[0][0][i] = tc0[i]; pc[0][1][i] = tc1[i]; }
+            else        { pl[1][i] = tl[i]; pc[1][0][i] = tc0[i]; pc[1][1][i] = tc1[i]; }
         }
     }
     uint8_t *Y = P.dst + (size_t)(y0 + by * ys) * W + x0 + bx;

@@ -97,13 +97,9 @@ __device__ inline int pred4x4_px(int mode, int x, int y, const int *nb, int &hav
 }
 
 // ---- 8x8 (qa: filtered samples, [0] corner, [1..8] left y=0..7, [9..24] top x=0..15) ----
-__device__ inline int pred8x8_px(int mode, int x, int y, const int *qa, int &have) {
+__device__ inline int pred8x8_px(int mode, int x, int y, const int *qa, int topok, int trok, int leftok, int cornok, int &have) {
 #define T(i) ((i) < 0 ? qa[0] : qa[9 + (i)])
 #define L(i) ((i) < 0 ? qa[0] : qa[1 + (i)])
-    int topok = 1, trok = 1, leftok = 1;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { if (qa[9 + i] < 0) topok = 0; if (qa[17 + i] < 0) trok = 0; if (qa[1 + i] < 0) leftok = 0; }
-    const int cornok = qa[0] >= 0;
     have = 0;
     switch (mode) {
     case 0: if (topok) { have = 1; return T(x); } break;
@@ -235,21 +231,23 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
 
     if (cls == H264B2_MB_I16x16) {                                      // PB:1847
         const int mode = I.pred16_chroma & 3;
-        if (lane < 16) S.nb[1 + lane] = sample(lane, -1, 0); else S.nb[17 + lane - 16] = sample(-1, lane - 16, 0);
+        const int nv = lane < 16 ? sample(lane, -1, 0) : sample(-1, lane - 16, 0);     // lanes 0-15 the row above, 16-31 the left column
+        S.nb[1 + lane] = nv;
         if (lane == 0) S.nb[0] = sample(-1, -1, 0);
+        const unsigned av = __ballot_sync(0xffffffffu, nv >= 0);
+        const int topok = (av & 0xFFFFu) == 0xFFFFu, leftok = (av >> 16) == 0xFFFFu;
+        const int sumT = __reduce_add_sync(0xffffffffu, lane < 16 ? nv : 0), sumL = __reduce_add_sync(0xffffffffu, lane < 16 ? 0 : nv);
         __syncwarp();
         const int *top = S.nb + 1, *left = S.nb + 17;
         const int corner = S.nb[0];
-        int topok = 1, leftok = 1;
-        for (int i = 0; i < 16; i++) { if (top[i] < 0) topok = 0; if (left[i] < 0) leftok = 0; }
         int have = 0, dcv = 128, aa = 0, bb = 0, cc = 0;
         if (mode == 0) have = topok;
         else if (mode == 1) have = leftok;
         else if (mode == 2) {
-            have = 1; int v = 0;
-            if (topok && leftok) { for (int i = 0; i < 16; i++) v += top[i] + left[i]; dcv = (v + 16) >> 5; }
-            else if (leftok) { for (int i = 0; i < 16; i++) v += left[i]; dcv = (v + 8) >> 4; }
-            else if (topok) { for (int i = 0; i < 16; i++) v += top[i]; dcv = (v + 8) >> 4; }
+            have = 1;
+            if (topok && leftok) dcv = (sumT + sumL + 16) >> 5;
+            else if (leftok) dcv = (sumL + 8) >> 4;
+            else if (topok) dcv = (sumT + 8) >> 4;
         } else if (topok && leftok) {                                   // the reference does not test p[-1,-1] here (PB:2014-2018)
             have = 1; int Hh = 0, V = 0;
             for (int i = 0; i < 8; i++) { Hh += (i + 1) * (top[8 + i] - (6 - i >= 0 ? top[6 - i] : corner)); V += (i + 1) * (left[8 + i] - (6 - i >= 0 ? left[6 - i] : corner)); }
@@ -265,42 +263,37 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
         for (int b = 0; b < 4; b++) {
             const int mode = (int)((modes >> (4 * b)) & 15);
             const int xO = (b & 1) * 8, yO = (b >> 1) * 8;
-            if (lane < 9) S.nb[lane] = sample(xO - 1, yO + lane - 1, 0);
-            else if (lane < 25) S.nb[lane] = sample(xO + lane - 9, yO - 1, 0);
-            __syncwarp();
-            {   // top-right substitution, then reference sample filtering 8.3.2.2.1 (PB:1536-1599); every lane computes one qa[]
-                int trmiss = 1;
-                for (int x = 8; x < 16; x++) if (S.nb[9 + x] >= 0) trmiss = 0;
-                const int sub = trmiss && S.nb[9 + 7] >= 0;
-#define PT(i) ((i) >= 8 && sub ? S.nb[9 + 7] : S.nb[9 + (i)])
-#define PL(i) (S.nb[1 + (i)])
-                const int pc = S.nb[0];
-                int top16 = 1, left8 = 1;
-                for (int x = 0; x < 16; x++) if (PT(x) < 0) top16 = 0;
-                for (int y = 0; y < 8; y++) if (PL(y) < 0) left8 = 0;
-                int v = -1;
+            // 25 neighbours, one per lane: lane 0 corner, lanes 1..8 left column, lanes 9..24 the 16 samples above
+            int v = -1;
+            if (lane < 9) v = sample(xO - 1, yO + lane - 1, 0);
+            else if (lane < 25) v = sample(xO + lane - 9, yO - 1, 0);
+            unsigned av = __ballot_sync(0xffffffffu, v >= 0);
+            const bool sub = !(av & 0x1FE0000u) && (av & 0x10000u);     // no top-right sample, p[7,-1] available: replicate it (PB:1516-1528)
+            const int v16 = __shfl_sync(0xffffffffu, v, 16);
+            if (sub && lane >= 17 && lane < 25) v = v16;
+            if (sub) av |= 0x1FE0000u;
+            const int top16 = ((av >> 9) & 0xFFFFu) == 0xFFFFu, left8 = ((av >> 1) & 0xFFu) == 0xFFu, cav = av & 1u;
+            {   // reference sample filtering 8.3.2.2.1 (PB:1536-1599): lane i produces filtered sample i from its neighbours' lanes
+                const int vm = __shfl_up_sync(0xffffffffu, v, 1), vp = __shfl_down_sync(0xffffffffu, v, 1);
+                const int pc = __shfl_sync(0xffffffffu, v, 0), pt0 = __shfl_sync(0xffffffffu, v, 9), pl0 = __shfl_sync(0xffffffffu, v, 1);
+                int q = -1;
                 if (lane == 0) {
-                    if (pc >= 0) {
-                        if (PT(0) < 0 || PL(0) < 0) { v = PT(0) >= 0 ? (3*pc + PT(0) + 2) >> 2 : PL(0) >= 0 ? (3*pc + PL(0) + 2) >> 2 : pc; }
-                        else v = (PT(0) + 2*pc + PL(0) + 2) >> 2;
+                    if (cav) {
+                        const int t0 = (av >> 9) & 1u, l0 = (av >> 1) & 1u;
+                        if (!t0 || !l0) q = t0 ? (3*pc + pt0 + 2) >> 2 : l0 ? (3*pc + pl0 + 2) >> 2 : pc;
+                        else q = (pt0 + 2*pc + pl0 + 2) >> 2;
                     }
                 } else if (lane < 9) {
-                    const int y = lane - 1;
-                    if (left8) v = y == 0 ? (pc >= 0 ? (pc + 2*PL(0) + PL(1) + 2) >> 2 : (3*PL(0) + PL(1) + 2) >> 2)
-                                 : y == 7 ? (PL(6) + 3*PL(7) + 2) >> 2 : (PL(y-1) + 2*PL(y) + PL(y+1) + 2) >> 2;
+                    if (left8) q = lane == 1 ? (cav ? (pc + 2*v + vp + 2) >> 2 : (3*v + vp + 2) >> 2) : lane == 8 ? (vm + 3*v + 2) >> 2 : (vm + 2*v + vp + 2) >> 2;
                 } else if (lane < 25) {
-                    const int x = lane - 9;
-                    if (top16) v = x == 0 ? (pc >= 0 ? (pc + 2*PT(0) + PT(1) + 2) >> 2 : (3*PT(0) + PT(1) + 2) >> 2)
-                                 : x == 15 ? (PT(14) + 3*PT(15) + 2) >> 2 : (PT(x-1) + 2*PT(x) + PT(x+1) + 2) >> 2;
+                    if (top16) q = lane == 9 ? (cav ? (pc + 2*v + vp + 2) >> 2 : (3*v + vp + 2) >> 2) : lane == 24 ? (vm + 3*v + 2) >> 2 : (vm + 2*v + vp + 2) >> 2;
                 }
-#undef PT
-#undef PL
-                if (lane < 25) S.qa[lane] = v;
+                if (lane < 25) S.qa[lane] = q;
             }
             __syncwarp();
             for (int i = lane; i < 64; i += 32) {
                 const int x = i & 7, y = i >> 3;
-                int have; const int pred = pred8x8_px(mode, x, y, S.qa, have);
+                int have; const int pred = pred8x8_px(mode, x, y, S.qa, top16, top16, left8, cav, have);
                 put(0, xO + x, yO + y, have, pred, res[(yO + y) * 16 + xO + x]);
             }
             __syncwarp();
@@ -330,14 +323,15 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
         const int comp = 1 + (lane >> 4), hl = lane & 15;
         int *nbc = S.nb + 17 * (lane >> 4);              // [0] corner, [1..8] top, [9..16] left
         __syncwarp();
-        if (hl < 8) nbc[1 + hl] = sample(hl, -1, comp); else nbc[9 + hl - 8] = sample(-1, hl - 8, comp);
+        const int nv = hl < 8 ? sample(hl, -1, comp) : sample(-1, hl - 8, comp);
+        nbc[1 + hl] = nv;                                    // [1..8] top, [9..16] left
         if (hl == 0) nbc[0] = sample(-1, -1, comp);
+        const unsigned av = (__ballot_sync(0xffffffffu, nv >= 0) >> (lane & 16)) & 0xFFFFu;
+        const int topok = (av & 0xFFu) == 0xFFu, leftok = (av >> 8) == 0xFFu;
         __syncwarp();
         const int *top = nbc + 1, *left = nbc + 9;
         const int corner = nbc[0];
         const int16_t *cres = res + 256 + (comp - 1) * 64;
-        int topok = 1, leftok = 1;
-        for (int i = 0; i < 8; i++) { if (top[i] < 0) topok = 0; if (left[i] < 0) leftok = 0; }
         int have = 0, aa = 0, bb = 0, cc = 0;
         if (cmode == 0) have = 1;
         else if (cmode == 1) have = leftok;
@@ -393,6 +387,7 @@ __device__ __forceinline__ bool intra_fast_ok(const PicDev &P, int a) {
 }
 
 // Wavefront driver (see wavefront.cuh): one CTA per band of WF_ROWS MB rows, one warp per row.
+template <bool GENERIC>
 __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ IntraWarpSmem sm[WF_ROWS];
     __shared__ int s_prog[WF_ROWS];
@@ -447,7 +442,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
                 const int a = (row * wmb + x) * per + s;
                 const H264B2MbInfo I = P.info[a];
                 if (I.mb_class >= H264B2_MB_I4x4 && I.mb_class <= H264B2_MB_IPCM) {
-                    if (intra_fast_ok(P, a)) intra_mb<true>(P, a, I, lane, sm[warp]); else intra_mb<false>(P, a, I, lane, sm[warp]);
+                    if (!GENERIC || intra_fast_ok(P, a)) intra_mb<true>(P, a, I, lane, sm[warp]); else intra_mb<false>(P, a, I, lane, sm[warp]);
                 }
             }
             rs_publish(rs, x + 1, lane);
