@@ -29,3 +29,16 @@ print("H2D GB/s", n / run(h2d) / 1e9)
 print("D2H GB/s", n / run(d2h) / 1e9)
 t = run(both); print("both: each direction GB/s", n / t / 1e9)
 print("H2D in 3.4MB chunks GB/s", n / run(chunks(150)) / 1e9)
+def chunks_d2h(k):
+    def f():
+        c = n // k
+        with torch.cuda.stream(s2):
+            for i in range(k): h2[i*c:(i+1)*c].copy_(d2[i*c:(i+1)*c], non_blocking=True)
+    return f
+def both_chunks(k):
+    a, b = chunks(k), chunks_d2h(k)
+    def f():
+        a(); b()
+    return f
+t = run(both_chunks(150)); print("both directions in 3.4MB chunks: each GB/s", n / t / 1e9)
+t = run(both_chunks(16)); print("both directions in 32MB chunks: each GB/s", n / t / 1e9)
