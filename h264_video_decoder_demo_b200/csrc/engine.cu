@@ -60,6 +60,34 @@ __global__ void k_snapshot(const uint8_t *const *src, uint8_t *dst, size_t n16) 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
 }
 
+// YUV420P -> BGR24 (the reference's integer BT.601 conversion, H264PictureBase.cpp:440-468 / FlipLines :471-498).
+// One thread = 4 horizontally adjacent pixels: one 32-bit luma load, 12 output bytes as three 32-bit stores.
+__global__ void k_bgr24(const uint8_t *i420, int W, int H, uint8_t *bgr, int width_bytes, int flip) {
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x4 * 4 >= W) return;
+    const uint32_t yy = *(const uint32_t *)(i420 + (size_t)y * W + x4 * 4);
+    const uint8_t *pu = i420 + (size_t)W * H + (size_t)(y >> 1) * (W >> 1) + x4 * 2, *pv = pu + (size_t)W * H / 4;
+    const int U0 = pu[0] - 128, U1 = pu[1] - 128, V0 = pv[0] - 128, V1 = pv[1] - 128;
+    uint8_t o[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int Y = 1164 * ((int)((yy >> (8 * i)) & 0xff) - 16), U = i < 2 ? U0 : U1, V = i < 2 ? V0 : V1;
+        o[3 * i + 0] = (uint8_t)clip255((Y + 2018 * U) / 1000);
+        o[3 * i + 1] = (uint8_t)clip255((Y - 813 * V - 391 * U) / 1000);
+        o[3 * i + 2] = (uint8_t)clip255((Y + 1596 * V) / 1000);
+    }
+    uint8_t *dst = bgr + (size_t)(flip ? H - 1 - y : y) * width_bytes + x4 * 12;
+    if ((((uintptr_t)dst) & 3) == 0) {
+        uint32_t *d32 = (uint32_t *)dst;
+        d32[0] = o[0] | (o[1] << 8) | (o[2] << 16) | ((uint32_t)o[3] << 24);
+        d32[1] = o[4] | (o[5] << 8) | (o[6] << 16) | ((uint32_t)o[7] << 24);
+        d32[2] = o[8] | (o[9] << 8) | (o[10] << 16) | ((uint32_t)o[11] << 24);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; i++) dst[i] = o[i];
+    }
+}
+
 // ------------------------------------------------------------------ context
 enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 6, MAX_GROUPS = 8 };
 
@@ -91,6 +119,7 @@ struct H264B2Context {
     uint8_t *out_stage[2]; size_t out_cap[2]; cudaEvent_t out_ready[2], out_done[2]; int out_next;
     uint8_t **d_ptrs; unsigned long long *d_sums; unsigned long long *h_sums; uint8_t **h_ptrs;
     uint8_t **h_snap[2], **h_snap_dev[2];     // mapped pinned pointer lists for k_snapshot
+    uint8_t *bgr; size_t bgr_cap;             // BGR24 output staging
     // timing
     cudaEvent_t t0, t1;
     int timing;
@@ -239,6 +268,7 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     if (!c) return fail(-1, "null context");
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->bgr) cudaFree(c->bgr);
     cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_snap[0]); cudaFreeHost(c->h_snap[1]);
     for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->compute_done[i]); }
     for (int i = 0; i < 2; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
@@ -531,6 +561,23 @@ extern "C" int h264b2_checksum_pictures(H264B2Context *c, int n, const int32_t *
 extern "C" int h264b2_checksum_picture(H264B2Context *c, int sid, int surface, uint64_t *sum) {
     const int32_t s = sid, f = surface;
     return h264b2_checksum_pictures(c, 1, &s, &f, sum);
+}
+
+// Output stage: convert a reconstructed surface to BGR24 on the GPU (what the reference's BMP writer and player
+// do on the CPU, H264PictureBase.cpp:525-548) and copy it to the host.  width_bytes >= 3*W (BMP rows are padded to
+// 4 bytes); flip_lines = 1 writes bottom-up like convertYuv420pToBgr24FlipLines.
+extern "C" int h264b2_read_picture_bgr24(H264B2Context *c, int sid, int surface, uint8_t *host_bgr24, int width_bytes, int flip_lines) {
+    uint8_t *p; int r = surf_ptr(c, sid, surface, &p); if (r) return r;
+    const int W = c->wmb * 16, H = c->hmb * 16;
+    if (!host_bgr24 || width_bytes < 3 * W) return fail(-1, "read_picture_bgr24: bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)width_bytes * H;
+    if (c->bgr_cap < bytes) { if (c->bgr) CK(cudaFree(c->bgr)); CK(cudaMalloc(&c->bgr, bytes)); c->bgr_cap = bytes; CK(cudaMemset(c->bgr, 0, bytes)); }
+    k_bgr24<<<dim3((W / 4 + 127) / 128, H), 128, 0, c->st>>>(p, W, H, c->bgr, width_bytes, flip_lines);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_bgr24, c->bgr, bytes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
 }
 
 // ------------------------------------------------------------------ memory helpers

@@ -27,6 +27,7 @@ _PROTOS = {
     "h264b2_submit_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(PicParams)]),
     "h264b2_read_picture": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "h264b2_read_pictures_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
+    "h264b2_read_picture_bgr24": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "h264b2_write_picture": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "h264b2_checksum_picture": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "h264b2_checksum_pictures": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
@@ -120,6 +121,12 @@ class Engine:
     def read_picture(self, stream_id: int, surface: int) -> np.ndarray:
         out = np.empty(self.frame_bytes, dtype=np.uint8)
         self._ck(self.lib.h264b2_read_picture(self._ctx, stream_id, surface, out.ctypes.data))
+        return out
+
+    def read_picture_bgr24(self, stream_id: int, surface: int, width_bytes: Optional[int] = None, flip_lines: bool = False) -> np.ndarray:
+        width_bytes = width_bytes or self.wmb * 48
+        out = np.empty(width_bytes * self.hmb * 16, dtype=np.uint8)
+        self._ck(self.lib.h264b2_read_picture_bgr24(self._ctx, stream_id, surface, out.ctypes.data, width_bytes, 1 if flip_lines else 0))
         return out
 
     def write_picture(self, stream_id: int, surface: int, data: np.ndarray):

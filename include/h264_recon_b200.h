@@ -166,6 +166,11 @@ int h264b2_read_picture(H264B2Context *ctx, int stream_id, int surface, uint8_t 
 int h264b2_read_pictures_async(H264B2Context *ctx, int n, const int32_t *stream_ids, const int32_t *surfaces,
                                uint8_t *const *host_i420);
 
+/* Output stage: the reference's integer BT.601 YUV420P -> BGR24 conversion
+ * (H264PictureBase.cpp:440-468; flip_lines = 1: the bottom-up twin :471-498 used for BMP files) done on the GPU,
+ * result copied to host_bgr24 (width_bytes >= 3 * width; rows beyond 3*width bytes are zero).  Synchronous. */
+int h264b2_read_picture_bgr24(H264B2Context *ctx, int stream_id, int surface, uint8_t *host_bgr24, int width_bytes, int flip_lines);
+
 /* Write a surface from host I420 (used by tests to seed reference pictures). */
 int h264b2_write_picture(H264B2Context *ctx, int stream_id, int surface, const uint8_t *host_i420);
 

@@ -27,6 +27,8 @@ def lib():
         _LIB.oracle_reconstruct_picture.restype = C.c_int
         _LIB.oracle_checksum.argtypes = [C.c_void_p, C.c_size_t]
         _LIB.oracle_checksum.restype = C.c_uint64
+        _LIB.oracle_convert_bgr24.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        _LIB.oracle_convert_bgr24.restype = C.c_int
     return _LIB
 
 
@@ -54,3 +56,11 @@ class OracleDPB:
     def checksum(self, slot):
         s = self.surfaces[slot]
         return int(lib().oracle_checksum(s.ctypes.data, s.size))
+
+
+def convert_bgr24(i420: np.ndarray, W: int, H: int, flip: bool = False) -> np.ndarray:
+    out = np.zeros(W * 3 * H, dtype=np.uint8)
+    src = np.ascontiguousarray(i420, dtype=np.uint8)
+    if lib().oracle_convert_bgr24(src.ctypes.data, W, H, out.ctypes.data, W * 3, 1 if flip else 0) != 0:
+        raise RuntimeError("oracle_convert_bgr24 failed")
+    return out

@@ -783,3 +783,19 @@ uint64_t oracle_checksum(const uint8_t *data, size_t bytes) {
     for (size_t i = 0; i < nw; i++) { uint32_t w; memcpy(&w, data + 4 * i, 4); acc += ((uint64_t)w + 1) * ((2 * (uint64_t)i + 1) * K); }
     return acc;
 }
+
+/* YUV420P -> BGR24, the reference's integer BT.601 conversion (H264PictureBase.cpp:440-468; the FlipLines twin :471-498
+ * writes row H-1-y).  C integer division truncates toward zero, exactly as in the reference. */
+int oracle_convert_bgr24(const uint8_t *i420, int W, int H, uint8_t *bgr, int width_bytes, int flip) {
+    if (!i420 || !bgr || W <= 0 || H <= 0 || width_bytes < 3 * W) return -1;
+    const uint8_t *pu = i420 + (size_t)W * H, *pv = pu + (size_t)W * H / 4;
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        const int Y = i420[(size_t)y * W + x], U = pu[(size_t)(y / 2) * (W / 2) + x / 2], V = pv[(size_t)(y / 2) * (W / 2) + x / 2];
+        const int b = (1164 * (Y - 16) + 2018 * (U - 128)) / 1000;
+        const int g = (1164 * (Y - 16) - 813 * (V - 128) - 391 * (U - 128)) / 1000;
+        const int r = (1164 * (Y - 16) + 1596 * (V - 128)) / 1000;
+        uint8_t *o = bgr + (size_t)(flip ? H - 1 - y : y) * width_bytes + 3 * x;
+        o[0] = (uint8_t)clip255(b); o[1] = (uint8_t)clip255(g); o[2] = (uint8_t)clip255(r);
+    }
+    return 0;
+}

@@ -49,7 +49,7 @@ static uint64_t checksum_pic(CH264PictureBase &f) {
 }
 
 // ---------------------------------------------------------------- state
-static FILE *g_yuv = nullptr, *g_replay = nullptr, *g_pixdump = nullptr;
+static FILE *g_yuv = nullptr, *g_replay = nullptr, *g_pixdump = nullptr, *g_bgr = nullptr;
 static int g_maxframes = 1 << 30, g_nframes = 0, g_quiet = 0;
 static int g_decode_idx = 0;
 static CH264Picture *g_cur_pic = nullptr;          // picture that received the last slice
@@ -371,6 +371,12 @@ static int cb(CH264Picture *pic, void *, int) {
         fwrite(f.m_pic_buff_cb, 1, (size_t)f.PicWidthInSamplesC * f.PicHeightInSamplesC, g_yuv);
         fwrite(f.m_pic_buff_cr, 1, (size_t)f.PicWidthInSamplesC * f.PicHeightInSamplesC, g_yuv);
     }
+    if (g_bgr) {    // the reference's own YUV420P -> BGR24 conversion (H264PictureBase.cpp:440), checksummed per output frame
+        const int W = f.PicWidthInSamplesL, H = f.PicHeightInSamplesL;
+        std::vector<uint8_t> bgr((size_t)W * 3 * H);
+        f.convertYuv420pToBgr24(W, H, f.m_pic_buff_luma, bgr.data(), W * 3);
+        fprintf(g_bgr, "%d %d %016llx %016llx\n", g_nframes, f.PicOrderCnt, (unsigned long long)h, (unsigned long long)checksum_bytes(bgr.data(), bgr.size(), 0, 0));
+    }
     if (g_replay) {
         auto it = g_pic2idx.find(pic);
         OutRec o; o.decode_idx = (it == g_pic2idx.end()) ? -1 : it->second; o.pad = 0; o.sum = h; g_out.push_back(o);
@@ -379,13 +385,14 @@ static int cb(CH264Picture *pic, void *, int) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 2) { fprintf(stderr, "usage: %s in.h264 [--yuv F] [--replay F] [--max-frames N] [--quiet] [--dump-pix IDX F]\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s in.h264 [--yuv F] [--replay F] [--max-frames N] [--quiet] [--bgr-sums F] [--dump-pix IDX F]\n", argv[0]); return 2; }
     const char *replay_path = nullptr;
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "--yuv") && i + 1 < argc) g_yuv = fopen(argv[++i], "wb");
         else if (!strcmp(argv[i], "--replay") && i + 1 < argc) { replay_path = argv[++i]; g_replay = fopen(replay_path, "wb"); }
         else if (!strcmp(argv[i], "--max-frames") && i + 1 < argc) g_maxframes = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--quiet")) g_quiet = 1;
+        else if (!strcmp(argv[i], "--bgr-sums") && i + 1 < argc) g_bgr = fopen(argv[++i], "w");
         else if (!strcmp(argv[i], "--dump-pix") && i + 2 < argc) { g_dump_pix_idx = atol(argv[++i]); g_pixdump = fopen(argv[++i], "wb"); }
     }
     struct FileHdr { char magic[8]; uint32_t version, width_mbs, height_mbs, n_pics, n_out, hdr_bytes, pichdr_bytes, reserved; } fh;
@@ -404,6 +411,7 @@ int main(int argc, char **argv) {
     }
     if (g_yuv) fclose(g_yuv);
     if (g_pixdump) fclose(g_pixdump);
+    if (g_bgr) fclose(g_bgr);
     fprintf(stderr, "RESULT file=%s ret=%d frames=%d pics=%d secs=%.3f fps=%.3f stream_hash=%016llx\n", argv[1], r, g_nframes, g_decode_idx, s, g_nframes / s,
             (unsigned long long)g_stream_hash);
     return 0;
