@@ -1,0 +1,142 @@
+// h264_front_internal.h — shared declarations of the host entropy/derivation stage (see include/h264_front_b200.h).
+// Bit reader, parameter sets, slice header, CABAC engine.  Plain C++17, no CUDA, no oracle.
+#pragma once
+#include "h264_front_b200.h"
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+namespace h264b2 {
+
+// ------------------------------------------------------------------ RBSP bit reader
+// Mirrors the observable behaviour of the reference's CBitstream (Bitstream.cpp:45-124): MSB first, the very last bit of a
+// buffer always reads as 0 (Bitstream.cpp:52-56 — applied once when the RBSP is extracted), more_rbsp_data() as
+// H264CommonFunc.cpp:71-123.  Reads past the end return 0 (the reference has undefined behaviour there).
+struct BitReader {
+    const uint8_t *d = nullptr;   // padded with >= 8 zero bytes
+    int64_t nbits = 0, pos = 0, last1 = -1;
+    void init(const uint8_t *data, size_t bytes) {
+        d = data; nbits = (int64_t)bytes * 8; pos = 0; last1 = -1;
+        for (int64_t i = (int64_t)bytes - 1; i >= 0; i--) if (data[i]) { int b = 0; while (!((data[i] >> b) & 1)) b++; last1 = i * 8 + (7 - b); break; }
+    }
+    // Past the end the reference shifts by a negative count (Bitstream.cpp:54, undefined behaviour); as compiled for x86-64
+    // that re-reads the last byte once every 32 reads (24 zeros, then the 8 bits of the last byte).  Reproduced so that
+    // truncated slices fail at the same syntax element (gop121's corrupt IDR).
+    uint32_t peek_slow(int k) const {
+        uint32_t v = 0;
+        const uint32_t last = nbits ? d[(nbits >> 3) - 1] : 0;
+        for (int i = 0; i < k; i++) {
+            const int64_t q = pos + i;
+            uint32_t b;
+            if (q < nbits) b = (d[q >> 3] >> (7 - (q & 7))) & 1;
+            else { const int r = (int)((q - nbits) & 31); b = r >= 24 ? (last >> (31 - r)) & 1 : 0; }
+            v = (v << 1) | b;
+        }
+        return v;
+    }
+    inline uint32_t peek(int k) const {          // k in [1, 32]
+        if (pos + k > nbits) return peek_slow(k);
+        const uint8_t *p = d + (pos >> 3);
+        uint64_t v = ((uint64_t)p[0] << 56) | ((uint64_t)p[1] << 48) | ((uint64_t)p[2] << 40) | ((uint64_t)p[3] << 32) | ((uint64_t)p[4] << 24) | ((uint64_t)p[5] << 16) | ((uint64_t)p[6] << 8) | p[7];
+        return (uint32_t)((v << (pos & 7)) >> (64 - k));
+    }
+    inline void skip(int k) { pos += k; }
+    inline uint32_t u(int k) { if (k == 0) return 0; uint32_t v = peek(k); pos += k; return v; }
+    inline uint32_t u1() { return u(1); }
+    inline uint32_t ue() {
+        uint32_t v = peek(32);
+        if (v == 0) { pos += 32; return 0xFFFFFFFFu; }      // > 31 leading zeros: not a valid code (H264Golomb.cpp:57 fails too)
+        int lz = __builtin_clz(v);
+        pos += lz + 1;
+        return lz ? ((1u << lz) - 1 + u(lz)) : 0;
+    }
+    inline int32_t se() { uint32_t k = ue(); int32_t v = (int32_t)((k + 1) >> 1); return (k & 1) ? v : -v; }
+    inline uint32_t te(int range) { if (range <= 0) return 0; if (range == 1) return !u1(); return ue(); }
+    inline bool more_rbsp_data() const { return pos < last1; }
+    inline bool aligned() const { return (pos & 7) == 0; }
+    inline bool exhausted() const { return pos >= nbits; }
+};
+
+// ------------------------------------------------------------------ parameter sets (fields the path needs)
+struct SPS {
+    int valid = 0;
+    int profile_idc = 0, constraint_set3_flag = 0, level_idc = 0, sps_id = 0, chroma_format_idc = 1, separate_colour_plane_flag = 0;
+    int bit_depth_luma_minus8 = 0, bit_depth_chroma_minus8 = 0, qpprime_y_zero_transform_bypass_flag = 0;
+    int seq_scaling_matrix_present_flag = 0, seq_scaling_list_present_flag[12] = {0};
+    int32_t ScalingList4x4[6][16], ScalingList8x8[6][64];
+    int UseDefault4x4[6] = {0}, UseDefault8x8[6] = {0};
+    int log2_max_frame_num_minus4 = 0, pic_order_cnt_type = 0, log2_max_pic_order_cnt_lsb_minus4 = 0;
+    int delta_pic_order_always_zero_flag = 0, offset_for_non_ref_pic = 0, offset_for_top_to_bottom_field = 0, num_ref_frames_in_pic_order_cnt_cycle = 0;
+    int offset_for_ref_frame[256];
+    int max_num_ref_frames = 0, gaps_in_frame_num_value_allowed_flag = 0, pic_width_in_mbs_minus1 = 0, pic_height_in_map_units_minus1 = 0;
+    int frame_mbs_only_flag = 1, mb_adaptive_frame_field_flag = 0, direct_8x8_inference_flag = 0;
+    int max_num_reorder_frames = -1;
+    // derived
+    int PicWidthInMbs = 0, PicHeightInMapUnits = 0, FrameHeightInMbs = 0, ChromaArrayType = 1, MaxFrameNum = 16, MaxPicOrderCntLsb = 16, ExpectedDeltaPerPicOrderCntCycle = 0;
+    SPS() { memset(ScalingList4x4, 0, sizeof ScalingList4x4); memset(ScalingList8x8, 0, sizeof ScalingList8x8); memset(offset_for_ref_frame, 0, sizeof offset_for_ref_frame); }
+};
+
+struct PPS {
+    int valid = 0;
+    int pps_id = 0, sps_id = 0, entropy_coding_mode_flag = 0, bottom_field_pic_order_in_frame_present_flag = 0, num_slice_groups_minus1 = 0;
+    int num_ref_idx_l0_default_active_minus1 = 0, num_ref_idx_l1_default_active_minus1 = 0, weighted_pred_flag = 0, weighted_bipred_idc = 0;
+    int pic_init_qp_minus26 = 0, pic_init_qs_minus26 = 0, chroma_qp_index_offset = 0, deblocking_filter_control_present_flag = 0;
+    int constrained_intra_pred_flag = 0, redundant_pic_cnt_present_flag = 0, transform_8x8_mode_flag = 0, pic_scaling_matrix_present_flag = 0;
+    int pic_scaling_list_present_flag[12] = {0};
+    int32_t ScalingList4x4[6][16], ScalingList8x8[6][64];
+    int UseDefault4x4[6] = {0}, UseDefault8x8[6] = {0};
+    int second_chroma_qp_index_offset = 0;
+    PPS() { memset(ScalingList4x4, 0, sizeof ScalingList4x4); memset(ScalingList8x8, 0, sizeof ScalingList8x8); }
+};
+
+enum { SLICE_P = 0, SLICE_B = 1, SLICE_I = 2, SLICE_SP = 3, SLICE_SI = 4 };
+
+struct Mmco { int op = 0, difference_of_pic_nums_minus1 = 0, long_term_pic_num = 0, long_term_frame_idx = 0, max_long_term_frame_idx_plus1 = 0; };
+
+struct SliceHeader {
+    int nal_ref_idc = 0, nal_unit_type = 0, IdrPicFlag = 0;
+    int first_mb_in_slice = 0, slice_type = 0, pps_id = 0, colour_plane_id = 0, frame_num = 0, field_pic_flag = 0, bottom_field_flag = 0, idr_pic_id = 0;
+    int pic_order_cnt_lsb = 0, delta_pic_order_cnt_bottom = 0, delta_pic_order_cnt[2] = {0, 0}, redundant_pic_cnt = 0, direct_spatial_mv_pred_flag = 0;
+    int num_ref_idx_active_override_flag = 0, num_ref_idx_l0_active_minus1 = 0, num_ref_idx_l1_active_minus1 = 0;
+    int ref_pic_list_modification_flag[2] = {0, 0}, modification_count[2] = {0, 0};
+    int modification_of_pic_nums_idc[2][33], abs_diff_pic_num_minus1[2][33], long_term_pic_num[2][33];
+    int luma_log2_weight_denom = 0, chroma_log2_weight_denom = 0;
+    int luma_weight[2][32], luma_offset[2][32], chroma_weight[2][32][2], chroma_offset[2][32][2];
+    int no_output_of_prior_pics_flag = 0, long_term_reference_flag = 0, adaptive_ref_pic_marking_mode_flag = 0, mmco_count = 0;
+    Mmco mmco[33];
+    int cabac_init_idc = 0, slice_qp_delta = 0, disable_deblocking_filter_idc = 0, slice_alpha_c0_offset_div2 = 0, slice_beta_offset_div2 = 0;
+    // derived
+    int SliceQPY = 0, MbaffFrameFlag = 0, PicHeightInMbs = 0, PicSizeInMbs = 0, MaxPicNum = 0, CurrPicNum = 0, FilterOffsetA = 0, FilterOffsetB = 0;
+    int32_t ScalingList4x4[6][16], ScalingList8x8[6][64];
+    SPS sps; PPS pps;               // snapshots, like the reference's m_sps / m_pps copies (H264SliceHeader.cpp:300-301)
+    SliceHeader() {
+        memset(modification_of_pic_nums_idc, 0, sizeof modification_of_pic_nums_idc); memset(abs_diff_pic_num_minus1, 0, sizeof abs_diff_pic_num_minus1);
+        memset(long_term_pic_num, 0, sizeof long_term_pic_num); memset(luma_weight, 0, sizeof luma_weight); memset(luma_offset, 0, sizeof luma_offset);
+        memset(chroma_weight, 0, sizeof chroma_weight); memset(chroma_offset, 0, sizeof chroma_offset);
+        memset(ScalingList4x4, 0, sizeof ScalingList4x4); memset(ScalingList8x8, 0, sizeof ScalingList8x8);
+    }
+};
+
+int parse_sps(BitReader &br, SPS &sps);
+int parse_pps(BitReader &br, PPS &pps, const SPS *spss);
+int parse_slice_header(BitReader &br, int nal_ref_idc, int nal_unit_type, const SPS *spss, const PPS *ppss, SliceHeader &sh);
+bool first_vcl_nal_of_picture(const SliceHeader &cur, const SliceHeader &last);
+
+// ------------------------------------------------------------------ CABAC arithmetic decoder (9.3.1.2, 9.3.3.2; H264Cabac.cpp:1041-1086, 2577-2824)
+struct Cabac {
+    BitReader *br = nullptr;
+    uint32_t range = 0, offset = 0;
+    uint8_t state[1024];          // (pStateIdx << 1) | valMPS
+    void init_contexts(int slice_type, int cabac_init_idc, int slice_qp);
+    void init_engine(BitReader *b) { br = b; range = 510; offset = br->u(9); }
+    int decision(int ctx);
+    inline int bypass() { offset = (offset << 1) | br->u1(); if (offset >= range) { offset -= range; return 1; } return 0; }
+    inline int terminate() {
+        range -= 2;
+        if (offset >= range) return 1;
+        if (range < 256) { int n = __builtin_clz(range) - 23; range <<= n; offset = (offset << n) | br->u(n); }
+        return 0;
+    }
+};
+
+}  // namespace h264b2
