@@ -15,19 +15,24 @@ HEADERS = ["common.cuh", "residual.cuh", "residual_kernel.cuh", "inter.cuh", "in
 
 HOST_LIB = os.path.join(_PKG, "libh264b2_host.so")
 HOST_CLI = os.path.join(_PKG, "h264b2_decode")
-HOST_SRC = os.path.join(CSRC, "host", "H264VideoDecoderB200.cpp")
+HOST_DIR = os.path.join(CSRC, "host")
+HOST_SRCS = [os.path.join(HOST_DIR, f) for f in ("H264VideoDecoderB200.cpp", "h264_front.cpp", "h264_slice.cpp", "h264_params.cpp")]
+HOST_HDRS = [os.path.join(HOST_DIR, f) for f in ("h264_front_internal.h", "h264_decoder.h", "h264_tables.inc")]
 CLI_SRC = os.path.join(_ROOT, "tools", "h264b2_decode.cpp")
+PARSE_CLI = os.path.join(_PKG, "h264b2_parse")
+PARSE_SRC = os.path.join(_ROOT, "tools", "h264b2_parse.cpp")
 
 
 def build_host(force=False):
     """The C++ host facade (CH264VideoDecoderB200) and its CLI: plain g++ over the C ABI, rpath = $ORIGIN."""
-    deps = [HOST_SRC, CLI_SRC, os.path.join(_ROOT, "include", "H264VideoDecoderB200.h"), os.path.join(_ROOT, "include", "h264_recon_b200.h"), LIB]
-    if not force and all(os.path.exists(x) and os.path.getmtime(x) >= max(os.path.getmtime(d) for d in deps) for x in (HOST_LIB, HOST_CLI)):
+    deps = HOST_SRCS + HOST_HDRS + [CLI_SRC, PARSE_SRC, LIB] + [os.path.join(_ROOT, "include", h) for h in ("H264VideoDecoderB200.h", "h264_recon_b200.h", "h264_front_b200.h")]
+    if not force and all(os.path.exists(x) and os.path.getmtime(x) >= max(os.path.getmtime(d) for d in deps) for x in (HOST_LIB, HOST_CLI, PARSE_CLI)):
         return HOST_LIB
-    inc = ["-I", os.path.join(_ROOT, "include")]
-    common = ["-O2", "-std=c++11", "-fPIC", "-Wall"] + inc
-    for cmd in (["g++"] + common + ["-shared", "-o", HOST_LIB, HOST_SRC, "-L", _PKG, "-lh264b2", "-Wl,-rpath,$ORIGIN"],
-                ["g++"] + common + ["-o", HOST_CLI, CLI_SRC, "-L", _PKG, "-lh264b2_host", "-lh264b2", "-Wl,-rpath,$ORIGIN"]):
+    inc = ["-I", os.path.join(_ROOT, "include"), "-I", HOST_DIR]
+    common = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-pthread"] + inc
+    for cmd in (["g++"] + common + ["-shared", "-o", HOST_LIB] + HOST_SRCS + ["-L", _PKG, "-lh264b2", "-Wl,-rpath,$ORIGIN"],
+                ["g++"] + common + ["-o", HOST_CLI, CLI_SRC, "-L", _PKG, "-lh264b2_host", "-lh264b2", "-Wl,-rpath,$ORIGIN"],
+                ["g++"] + common + ["-o", PARSE_CLI, PARSE_SRC, "-L", _PKG, "-lh264b2_host", "-lh264b2", "-Wl,-rpath,$ORIGIN"]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

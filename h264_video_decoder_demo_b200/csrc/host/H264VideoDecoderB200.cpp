@@ -2,6 +2,11 @@
 // (h264_recon_b200.h); no CUDA headers, no oracle, no CPU reconstruction.
 #include "H264VideoDecoderB200.h"
 #include "h264_recon_b200.h"
+#include "h264_front_b200.h"
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -41,14 +46,14 @@ int CH264VideoDecoderB200::open(const char *url) {
     size_t next_out = 0;
     FileHdr fh;
     if (!url) { snprintf(m_error, sizeof m_error, "open: null url"); return -1; }
-    {
-        const size_t n = strlen(url);
-        if (n > 5 && (!strcmp(url + n - 5, ".h264") || !strcmp(url + n - 4, ".264")))
-            FAIL(-2, "open: %s is a raw byte stream; the native entropy front end is not part of this build (feed a pre-parsed picture container); no CPU fallback", url);
-    }
     f = fopen(url, "rb");
     if (!f) FAIL(-1, "open: cannot open %s", url);
-    if (fread(&fh, sizeof fh, 1, f) != 1 || memcmp(fh.magic, "H264B2RP", 8) || fh.version != 1 || fh.hdr_bytes != sizeof fh || fh.pichdr_bytes != sizeof(PicHdr))
+    if (fread(&fh, sizeof fh, 1, f) != 1 || memcmp(fh.magic, "H264B2RP", 8)) {
+        // not a pre-parsed container: an Annex-B byte stream, like the reference's open() takes (H264VideoDecoder.cpp:48)
+        fclose(f); f = nullptr;
+        return open_bitstream(url);
+    }
+    if (fh.version != 1 || fh.hdr_bytes != sizeof fh || fh.pichdr_bytes != sizeof(PicHdr))
         FAIL(-1, "open: %s is not a picture container", url);
     {
         if (fseek(f, 0, SEEK_END)) FAIL(-1, "open: seek failed");
@@ -113,6 +118,91 @@ int CH264VideoDecoderB200::open(const char *url) {
 done:
     if (f) fclose(f);
     if (ctx) { if (frame) h264b2_host_free(ctx, frame); if (blob) h264b2_host_free(ctx, blob); h264b2_destroy(ctx); }
+    return ret;
+}
+
+// ---- Annex-B path: host entropy/derivation stage (h264_front_b200.h) on a producer thread, GPU reconstruction and the
+// output callback on the calling thread (the reference invokes the callback synchronously on the caller, VD:396-432).
+namespace {
+struct PinCtx { H264B2Context *ctx; };
+void *pin_alloc(void *u, size_t n) { void *p = nullptr; return h264b2_host_alloc(((PinCtx *)u)->ctx, n, &p) == 0 ? p : nullptr; }
+void pin_free(void *u, void *p) { h264b2_host_free(((PinCtx *)u)->ctx, p); }
+struct EvQueue {
+    std::mutex mu; std::condition_variable cv; std::deque<H264B2FrontEvent> q; bool done = false, cancel = false; int err = 0;
+    void push(const H264B2FrontEvent &e) { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return q.size() < 12 || cancel; }); q.push_back(e); cv.notify_all(); }
+    bool pop(H264B2FrontEvent *e) { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !q.empty() || done; }); if (q.empty()) return false; *e = q.front(); q.pop_front(); cv.notify_all(); return true; }
+};
+}
+
+int CH264VideoDecoderB200::open_bitstream(const char *url) {
+    int ret = 0;
+    H264B2Context *ctx = nullptr;
+    H264B2Front *fe = nullptr, *probe = nullptr;
+    uint8_t *frame = nullptr;
+    PinCtx pc = {nullptr};
+    EvQueue Q;
+    std::thread producer;
+    std::deque<void *> inflight;       // picture blocks whose DMA may still be pending (h264b2_submit keeps 3 batches in flight)
+    int wmb = 0, hmb = 0, n_frames = 0;
+    H264B2FrontEvent ev;
+    // picture size: parse up to the first picture with a throw-away front end (the context needs the size up front)
+    if (h264b2_front_create(&probe, nullptr, nullptr, nullptr) || h264b2_front_open_file(probe, url)) FAIL(-1, "open: %s", probe ? h264b2_front_last_error(probe) : "out of memory");
+    for (;;) {
+        if (h264b2_front_next(probe, &ev) < 0) FAIL(-1, "open: %s", h264b2_front_last_error(probe));
+        if (ev.kind == H264B2_EV_PICTURE) { wmb = ev.width_mbs; hmb = ev.height_mbs; break; }
+        if (ev.kind == H264B2_EV_END) FAIL(-1, "open: %s holds no decodable picture", url);
+    }
+    h264b2_front_destroy(probe); probe = nullptr;
+    if (h264b2_create(&ctx, m_device, 1, 17, wmb, hmb)) FAIL(-3, "open: %s", h264b2_last_error());
+    pc.ctx = ctx;
+    if (h264b2_host_alloc(ctx, (size_t)wmb * hmb * 384, (void **)&frame)) FAIL(-3, "open: %s", h264b2_last_error());
+    if (h264b2_front_create(&fe, pin_alloc, pin_free, &pc) || h264b2_front_open_file(fe, url)) FAIL(-1, "open: %s", fe ? h264b2_front_last_error(fe) : "out of memory");
+    producer = std::thread([&] {
+        for (;;) {
+            H264B2FrontEvent e;
+            const int r = h264b2_front_next(fe, &e);
+            if (r < 0) { std::lock_guard<std::mutex> l(Q.mu); Q.err = r; Q.done = true; Q.cv.notify_all(); return; }
+            Q.push(e);
+            if (e.kind == H264B2_EV_END || Q.cancel) { std::lock_guard<std::mutex> l(Q.mu); Q.done = true; Q.cv.notify_all(); return; }
+        }
+    });
+    {
+        const int W = wmb * 16, H = hmb * 16;
+        std::vector<int> surf_poc(17, 0), surf_idx(17, 0), surf_type(17, 0), surf_mbaff(17, 0);
+        bool ended = false;
+        while (Q.pop(&ev)) {
+            if (ev.kind == H264B2_EV_PICTURE) {
+                const int32_t sid = 0;
+                if (!ev.block) { ret = -3; snprintf(m_error, sizeof m_error, "open: out of page-locked memory"); break; }
+                if (h264b2_submit(ctx, 1, &sid, &ev.params)) { ret = -3; snprintf(m_error, sizeof m_error, "open: %s", h264b2_last_error()); break; }
+                inflight.push_back(ev.block);
+                while (inflight.size() > 3) { h264b2_front_release(fe, inflight.front()); inflight.pop_front(); }
+                surf_poc[ev.surface] = ev.hdr.poc; surf_idx[ev.surface] = ev.decode_idx; surf_type[ev.surface] = ev.hdr.slice_type; surf_mbaff[ev.surface] = ev.hdr.mbaff;
+            } else if (ev.kind == H264B2_EV_OUTPUT) {
+                if (h264b2_read_picture(ctx, 0, ev.surface, frame)) { ret = -3; snprintf(m_error, sizeof m_error, "open: %s", h264b2_last_error()); break; }
+                CH264PictureB200 out; memset(&out, 0, sizeof out);
+                CH264PictureBaseB200 &b = out.m_picture_frame;
+                b.m_pic_buff_luma = frame; b.m_pic_buff_cb = frame + (size_t)W * H; b.m_pic_buff_cr = b.m_pic_buff_cb + (size_t)(W / 2) * (H / 2);
+                b.PicWidthInSamplesL = W; b.PicHeightInSamplesL = H; b.PicWidthInSamplesC = W / 2; b.PicHeightInSamplesC = H / 2;
+                b.PicOrderCnt = surf_poc[ev.surface]; b.m_PicNumCnt = surf_idx[ev.surface]; b.slice_type = surf_type[ev.surface]; b.MbaffFrameFlag = surf_mbaff[ev.surface];
+                n_frames++;
+                if (m_output_frame_callback && m_output_frame_callback(&out, m_userData, H264_DECODE_ERROR_CODE_NO) != 0) break;      // VD:119-124: stop
+            } else { ended = true; break; }
+        }
+        { std::lock_guard<std::mutex> l(Q.mu); Q.cancel = true; Q.cv.notify_all(); }
+        // drain so that the producer can finish
+        while (Q.pop(&ev)) { if (ev.kind == H264B2_EV_PICTURE && ev.block) h264b2_front_release(fe, ev.block); }
+        if (producer.joinable()) producer.join();
+        if (!ret && Q.err) { ret = -1; snprintf(m_error, sizeof m_error, "open: %s", h264b2_front_last_error(fe)); }
+        if (!ret && ended && m_output_frame_callback) m_output_frame_callback(nullptr, m_userData, H264_DECODE_ERROR_CODE_FILE_END);   // VD:372-374
+    }
+done:
+    if (producer.joinable()) { { std::lock_guard<std::mutex> l(Q.mu); Q.cancel = true; Q.cv.notify_all(); } while (Q.pop(&ev)) {} producer.join(); }
+    if (probe) h264b2_front_destroy(probe);
+    if (ctx) h264b2_sync(ctx);
+    if (fe) h264b2_front_destroy(fe);
+    if (ctx) { if (frame) h264b2_host_free(ctx, frame); h264b2_destroy(ctx); }
+    (void)n_frames;
     return ret;
 }
 

@@ -10,9 +10,10 @@
  * and valid only during the callback (H264VideoDecoder.cpp:407, 431); Y, Cb and Cr are contiguous in one
  * allocation exactly like the reference's (H264PictureBase.cpp:167-179).
  *
- * Round-1 scope: open() takes a PRE-PARSED picture container (the output of the serial host entropy stage:
- * per-picture structure-of-arrays, see h264_recon_b200.h) — the native CAVLC/CABAC front end is the next row
- * of the build plan.  Opening a raw .h264 byte stream returns -2 and says so; there is no CPU fallback.
+ * open() takes an Annex-B byte stream: the serial host stage (h264_front_b200.h: NAL split, CAVLC/CABAC, every
+ * neighbour-dependent derivation, DPB/output bookkeeping) runs on a producer thread and feeds per-picture
+ * structure-of-arrays to the CUDA engine (h264_recon_b200.h); all pixel work happens on the GPU — there is no CPU
+ * reconstruction fallback.  A pre-parsed picture container (tools/h264b2_parse, oracle/ref_harness) is accepted too.
  */
 #ifndef H264_VIDEO_DECODER_B200_H
 #define H264_VIDEO_DECODER_B200_H
@@ -37,9 +38,10 @@ public:
     int unInit();
     int set_output_frame_callback_functuin(output_frame_callback_b200 output_frame_callback, void *userData);   /* sic: the reference's spelling */
     int set_device(int device);                 /* which GPU (default 0) */
-    int open(const char *url);
+    int open(const char *url);                  /* an Annex-B .h264 byte stream (like the reference) or a pre-parsed picture container */
     const char *last_error() const { return m_error; }
 private:
+    int open_bitstream(const char *url);
     output_frame_callback_b200 m_output_frame_callback;
     void *m_userData;
     int m_device;

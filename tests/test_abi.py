@@ -29,6 +29,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.h264b2_abi_version() == abi.ABI_VERSION
 
 
+def test_host_library_exports_every_front_end_and_decoder_symbol():
+    from h264_video_decoder_demo_b200 import frontend
+    lib = frontend.lib()
+    for hdr, prefix in (("h264_front_b200.h", r"h264b2_front_[a-z0-9_]+"), ("H264VideoDecoderB200.h", r"h264b2_decoder_[a-z0-9_]+")):
+        txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", hdr)).read(), flags=re.S)
+        syms = sorted(set(re.findall(r"\b(" + prefix + r")\s*\(", txt)))
+        assert len(syms) >= 6
+        for s in syms:
+            assert hasattr(lib, s), f"libh264b2_host.so does not export {s}"
+
+
 def test_struct_layouts_match_c():
     src = r'''
 #include <stdio.h>
