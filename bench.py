@@ -185,6 +185,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-mode", default="full", choices=["full", "h2d", "d2h"], help="diagnostic: which PCIe legs the e2e loop includes")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bitstream", action="store_true", help="skip the Annex-B-in / frames-out pipeline measurement")
+    ap.add_argument("--bitstream-streams", type=int, default=32, help="streams per GPU of the Annex-B pipeline measurement")
+    ap.add_argument("--bitstream-threads", type=int, default=0, help="parser threads (0 = usable host cores / ranks)")
     ap.add_argument("--max-pictures", type=int, default=None)
     args = ap.parse_args()
     stems = [WORKLOADS[w] for w in (MIXED if args.workload == "mixed" else [args.workload])]
@@ -363,6 +366,30 @@ def main():
                "steps": args.e2e_steps, "device_ms_per_step": round(e2e_dev_ms / args.e2e_steps, 1),
                "kernel_ms_per_step": {k: round(v["ms"] / args.e2e_steps, 1) for k, v in e2e_kt.items()}, "timing": "host wall clock around submit+read-back of every picture, synchronised on both sides, max over ranks"}
 
+    l2_gb = (sum(sum(r.blob_bytes) for r in rs) + 17 * eng.frame_bytes * S) / 1e9
+    # ---- the whole decoder: Annex-B in, pictures out (host entropy/derivation stage on a thread pool + the CUDA engine)
+    e2e_bits = None
+    stream_files = [os.path.join(REF_DIR, "streams", st + ".h264") for st in stems]
+    if not args.no_bitstream and all(os.path.exists(f) for f in stream_files):
+        from h264_video_decoder_demo_b200 import frontend
+        eng.close()
+        nstr = args.bitstream_streams
+        threads = args.bitstream_threads or max(1, usable_cores() // world)
+        paths = [stream_files[i % len(stream_files)] for i in range(nstr)]
+        hashes_want = [frontend.hash_chain(variants[i % len(variants)]["rp"].out_sums) for i in range(nstr)] if is_full and args.max_pictures is None else None
+        frontend.multi_decode(paths[:min(nstr, 4)], device=local_rank, threads=min(threads, 4), readback=True, hashes=False)      # warm-up (page-locked pools, clocks)
+        sharding.barrier()
+        st_b, hs = frontend.multi_decode(paths, device=local_rank, threads=threads, readback=True, hashes=True)
+        if hashes_want is not None and hs != hashes_want:
+            raise SystemExit("PARITY FAILURE in the Annex-B pipeline: output frames differ from the reference decoder's")
+        secs = sharding.max_over_ranks(st_b["seconds"])
+        e2e_bits = {"value": round(st_b["frames_out"] * world / secs, 1), "unit": UNIT, "streams_per_gpu": nstr, "parser_threads_per_gpu": st_b["threads"],
+                    "host_cores": usable_cores(), "frames": st_b["frames_out"] * world, "seconds": round(secs, 3),
+                    "host_stage_pictures_per_s_per_thread": round(st_b["pictures"] / st_b["parse_seconds"], 1) if st_b["parse_seconds"] > 0 else None,
+                    "h2d_bytes": st_b["h2d_bytes"], "d2h_bytes": st_b["d2h_bytes"], "submits": st_b["submits"],
+                    "checked": "every stream's output-order checksum chain equals the reference decoder's" if hashes_want is not None else "not checked (prefix fixtures)",
+                    "what": "h264b2_multi_decode: Annex-B byte streams in, every output picture in page-locked host memory; host entropy decoding + derivations included"}
+
     # ---- CPU baseline: the unmodified reference on one host core (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -382,9 +409,9 @@ def main():
                                     f"all {len(stems)} bundled streams ({', '.join(stems)}) dealt round-robin over {S} concurrent streams per GPU")
                                    + ("" if is_full else " (golden prefix only: full replay not built)"),
                        "pictures_per_step_per_gpu": S * npic, "streams_per_gpu": S, "picture": "1920x1088 I420",
-                       "l2": "inputs larger than L2: one distinct SoA copy + 17-surface DPB per stream (%.1f GB per GPU)" % ((sum(sum(r.blob_bytes) for r in rs) + 17 * eng.frame_bytes * S) / 1e9),
+                       "l2": "inputs larger than L2: one distinct SoA copy + 17-surface DPB per stream (%.1f GB per GPU)" % l2_gb,
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_bitstream": e2e_bits, "gpu_launches": launches, "clocks": clocks,
         }) + "\n").encode())
     if world > 1:
         import torch.distributed as dist

@@ -16,7 +16,7 @@ HEADERS = ["common.cuh", "residual.cuh", "residual_kernel.cuh", "inter.cuh", "in
 HOST_LIB = os.path.join(_PKG, "libh264b2_host.so")
 HOST_CLI = os.path.join(_PKG, "h264b2_decode")
 HOST_DIR = os.path.join(CSRC, "host")
-HOST_SRCS = [os.path.join(HOST_DIR, f) for f in ("H264VideoDecoderB200.cpp", "h264_front.cpp", "h264_slice.cpp", "h264_params.cpp")]
+HOST_SRCS = [os.path.join(HOST_DIR, f) for f in ("H264VideoDecoderB200.cpp", "h264_front.cpp", "h264_slice.cpp", "h264_params.cpp", "h264_multi.cpp")]
 HOST_HDRS = [os.path.join(HOST_DIR, f) for f in ("h264_front_internal.h", "h264_decoder.h", "h264_tables.inc")]
 CLI_SRC = os.path.join(_ROOT, "tools", "h264b2_decode.cpp")
 PARSE_CLI = os.path.join(_PKG, "h264b2_parse")
@@ -25,7 +25,7 @@ PARSE_SRC = os.path.join(_ROOT, "tools", "h264b2_parse.cpp")
 
 def build_host(force=False):
     """The C++ host facade (CH264VideoDecoderB200) and its CLI: plain g++ over the C ABI, rpath = $ORIGIN."""
-    deps = HOST_SRCS + HOST_HDRS + [CLI_SRC, PARSE_SRC, LIB] + [os.path.join(_ROOT, "include", h) for h in ("H264VideoDecoderB200.h", "h264_recon_b200.h", "h264_front_b200.h")]
+    deps = HOST_SRCS + HOST_HDRS + [CLI_SRC, PARSE_SRC, LIB] + [os.path.join(_ROOT, "include", h) for h in ("H264VideoDecoderB200.h", "h264_recon_b200.h", "h264_front_b200.h", "h264_multi_b200.h")]
     if not force and all(os.path.exists(x) and os.path.getmtime(x) >= max(os.path.getmtime(d) for d in deps) for x in (HOST_LIB, HOST_CLI, PARSE_CLI)):
         return HOST_LIB
     inc = ["-I", os.path.join(_ROOT, "include"), "-I", HOST_DIR]

@@ -40,18 +40,28 @@ struct Dec {
 
     // ------------------------------------------------------------ neighbouring locations (6.4.12; PB:2878-3395)
     inline bool same_slice(int a, int c) const { return mbs[a].slice == mbs[c].slice; }
+    // non-MBAFF: the four neighbouring macroblock addresses of the current macroblock are derived once per macroblock
+    mutable int nc_mb = -1, nc_slice = -1, nA_ = -1, nB_ = -1, nC_ = -1, nD_ = -1;
+    inline void nbr_cache(int c) const {
+        nc_mb = c; nc_slice = mbs[c].slice;
+        const int col = c % W;
+        int n;
+        n = c - 1; nA_ = (n < 0 || col == 0 || !same_slice(n, c)) ? -1 : n;
+        n = c - W; nB_ = (n < 0 || !same_slice(n, c)) ? -1 : n;
+        n = c - W + 1; nC_ = (n < 0 || col == W - 1 || !same_slice(n, c)) ? -1 : n;
+        n = c - W - 1; nD_ = (n < 0 || col == 0 || !same_slice(n, c)) ? -1 : n;
+    }
     Nb nbr(int c, int xN, int yN, bool chroma) const {
         const int maxW = chroma ? 8 : 16, maxH = chroma ? 8 : 16;
         Nb r; r.mb = -1; r.xW = 0; r.yW = 0;
         if (yN > maxH - 1) return r;
         if (!mbaff) {
-            int n = -1;
-            if (xN < 0 && yN < 0) { n = c - W - 1; if (n < 0 || !same_slice(n, c) || c % W == 0) n = -1; }
-            else if (xN < 0) { n = c - 1; if (n < 0 || !same_slice(n, c) || c % W == 0) n = -1; }
-            else if (xN <= maxW - 1 && yN < 0) { n = c - W; if (n < 0 || !same_slice(n, c)) n = -1; }
-            else if (xN <= maxW - 1) n = c;
-            else if (yN < 0) { n = c - W + 1; if (n < 0 || !same_slice(n, c) || (c + 1) % W == 0) n = -1; }
-            r.mb = n; r.xW = (xN + maxW) % maxW; r.yW = (yN + maxH) % maxH;
+            if (c != nc_mb || mbs[c].slice != nc_slice) nbr_cache(c);
+            int n;
+            if (xN < 0) n = yN < 0 ? nD_ : nA_;
+            else if (xN <= maxW - 1) n = yN < 0 ? nB_ : c;
+            else n = yN < 0 ? nC_ : -1;
+            r.mb = n; r.xW = (xN + maxW) & (maxW - 1); r.yW = (yN + maxH) & (maxH - 1);
             return r;
         }
         // MBAFF (Table 6-4)
@@ -459,16 +469,19 @@ struct Dec {
 
     // ------------------------------------------------------------ residual() (MB:1677-1856; bookkeeping quirks Q18 kept)
     int last_run_before = 0;
+    uint32_t coded = 0;          // H264B2_CM_*-style mask of blocks that were parsed with TotalCoeff > 0
     int residual() {
         MbT &m = mbs[cur];
         int total = 0;
         last_run_before = 0;
-        // residual_luma works on scratch arrays and the reference copies them to the macroblock only on success (MB:1693-1697)
-        int32_t t_dc[16], t_ac[16][16], t_l4[16][16], t_l8[4][64];
-        memset(t_dc, 0, sizeof t_dc); memset(t_ac, 0, sizeof t_ac); memset(t_l4, 0, sizeof t_l4); memset(t_l8, 0, sizeof t_l8);
+        // residual_luma works on scratch arrays and the reference copies them to the macroblock only on success (MB:1693-1697):
+        // a failing macroblock keeps all-zero levels — emit_mb() is told through residual_ok.  `coded` marks the blocks that were parsed.
+        int32_t (&t_dc)[16] = i16dc; int32_t (&t_ac)[16][16] = i16ac; int32_t (&t_l4)[16][16] = l4; int32_t (&t_l8)[4][64] = l8;
+        coded = 0;
         if (m.type == T_I16) {
             if (residual_block(t_dc, 0, 15, 16, CAT_I16DC, 0, -1, &total)) return -1;
             m.nnz[0] = (uint8_t)total;
+            if (total) coded |= 1u << 16;
         }
         for (int i8 = 0; i8 < 4; i8++) {
             if (!m.t8x8 || !cabac) {
@@ -479,23 +492,25 @@ struct Dec {
                         else if (residual_block(t_l4[b], 0, 15, 16, CAT_LUMA4, b, -1, &total)) return -1;
                         m.nnz[b] = (uint8_t)total;
                         m.nnz8[i8] = (uint8_t)(m.nnz8[i8] + m.nnz[b]);
+                        if (total) coded |= 1u << (m.t8x8 ? i8 : b);
                     }
                     if (!cabac && m.t8x8) {
-                        for (int i = 0; i < 16; i++) t_l8[i8][4 * i + i4] = t_l4[b][i];
+                        if (m.cbp_luma & (1 << i8)) for (int i = 0; i < 16; i++) t_l8[i8][4 * i + i4] = t_l4[b][i];
                         m.nnz8[i8] = (uint8_t)(m.nnz8[i8] + m.nnz[b]);
                     }
                 }
             } else if (m.cbp_luma & (1 << i8)) {
                 total = residual_block_cabac(t_l8[i8], 0, 63, 64, CAT_LUMA8, i8, -1);
                 m.nnz8[i8] = (uint8_t)total;
+                if (total) coded |= 1u << i8;
             }
         }
-        memcpy(i16dc, t_dc, sizeof t_dc); memcpy(i16ac, t_ac, sizeof t_ac); memcpy(l4, t_l4, sizeof t_l4); memcpy(l8, t_l8, sizeof t_l8);
         last_run_before = 0;        // the chroma blocks use another decoder object (MB:1685)
         for (int c = 0; c < 2; c++) {
             if (m.cbp_chroma & 3) {
                 if (residual_block(cdc[c], 0, 3, 4, CAT_CDC, 0, c, &total)) return -1;
                 m.nnz_c[c][0] = (uint8_t)total;
+                if (total) coded |= 1u << 17;
             } else memset(cdc[c], 0, sizeof cdc[c]);
         }
         for (int c = 0; c < 2; c++)
@@ -503,7 +518,8 @@ struct Dec {
                 if (m.cbp_chroma & 2) {
                     if (residual_block(cac[c][b], 0, 14, 15, CAT_CAC, b, c, &total)) return -1;
                     m.nnz_c[c][b] = (uint8_t)total;
-                } else memset(cac[c][b], 0, sizeof(int32_t) * 15);
+                    if (total) coded |= 1u << (18 + 4 * c + b);
+                }
             }
         return 0;
     }
@@ -957,7 +973,11 @@ struct Dec {
     // ------------------------------------------------------------ SoA emission of one macroblock
     static bool anynz(const int32_t *s, int n) { for (int i = 0; i < n; i++) if (s[i]) return true; return false; }
     void put16(const int32_t *src, int n, int shift_in) {
-        for (int k = 0; k < n; k++) { int32_t v = shift_in ? (k == 0 ? 0 : src[k - 1]) : src[k]; v = v < -32768 ? -32768 : v > 32767 ? 32767 : v; F.coefs.push_back((int16_t)v); }
+        const size_t o = F.coefs.size();
+        F.coefs.resize(o + n);
+        int16_t *dst = F.coefs.data() + o;
+        if (shift_in) { dst[0] = 0; for (int k = 1; k < n; k++) { int32_t v = src[k - 1]; dst[k] = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); } }
+        else for (int k = 0; k < n; k++) { int32_t v = src[k]; dst[k] = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
     }
     void emit_mb(bool have_residual) {
         const MbT &m = mbs[cur];
@@ -975,15 +995,17 @@ struct Dec {
         I.filter_offset_a = (int8_t)sh.FilterOffsetA; I.filter_offset_b = (int8_t)sh.FilterOffsetB; I.deblock_idc = (uint8_t)sh.disable_deblocking_filter_idc;
         uint32_t cm = 0;
         if (m.cls == H264B2_MB_IPCM) { cm |= H264B2_CM_PCM; for (int i = 0; i < 384; i++) F.coefs.push_back(pcm[i]); }
-        else if (have_residual) {
+        else if (have_residual && coded) {
+            // a block is present iff it has a non-zero level (oracle/ref_harness.cpp); only parsed blocks (TotalCoeff > 0) can have one
+            const uint32_t cd = coded;
             if (m.cls == H264B2_MB_I16x16) {
-                for (int b = 0; b < 16; b++) if (anynz(i16ac[b], 15)) { cm |= H264B2_CM_LUMA(b); put16(i16ac[b], 16, 1); }
-                if (anynz(i16dc, 16)) { cm |= H264B2_CM_LUMA_DC; put16(i16dc, 16, 0); }
-            } else if (m.t8x8) { for (int b = 0; b < 4; b++) if (anynz(l8[b], 64)) { cm |= H264B2_CM_LUMA(b); put16(l8[b], 64, 0); } }
-            else for (int b = 0; b < 16; b++) if (anynz(l4[b], 16)) { cm |= H264B2_CM_LUMA(b); put16(l4[b], 16, 0); }
-            if (anynz(cdc[0], 4) || anynz(cdc[1], 4)) { cm |= H264B2_CM_CHROMA_DC; put16(cdc[0], 4, 0); put16(cdc[1], 4, 0); }
-            for (int b = 0; b < 4; b++) if (anynz(cac[0][b], 15)) { cm |= H264B2_CM_CB(b); put16(cac[0][b], 16, 1); }
-            for (int b = 0; b < 4; b++) if (anynz(cac[1][b], 15)) { cm |= H264B2_CM_CR(b); put16(cac[1][b], 16, 1); }
+                for (int b = 0; b < 16; b++) if ((cd >> b) & 1) if (anynz(i16ac[b], 15)) { cm |= H264B2_CM_LUMA(b); put16(i16ac[b], 16, 1); }
+                if ((cd >> 16) & 1) if (anynz(i16dc, 16)) { cm |= H264B2_CM_LUMA_DC; put16(i16dc, 16, 0); }
+            } else if (m.t8x8) { for (int b = 0; b < 4; b++) if ((cd >> b) & 1) if (anynz(l8[b], 64)) { cm |= H264B2_CM_LUMA(b); put16(l8[b], 64, 0); } }
+            else for (int b = 0; b < 16; b++) if ((cd >> b) & 1) if (anynz(l4[b], 16)) { cm |= H264B2_CM_LUMA(b); put16(l4[b], 16, 0); }
+            if ((cd >> 17) & 1) if (anynz(cdc[0], 4) || anynz(cdc[1], 4)) { cm |= H264B2_CM_CHROMA_DC; put16(cdc[0], 4, 0); put16(cdc[1], 4, 0); }
+            for (int b = 0; b < 4; b++) if ((cd >> (18 + b)) & 1) if (anynz(cac[0][b], 15)) { cm |= H264B2_CM_CB(b); put16(cac[0][b], 16, 1); }
+            for (int b = 0; b < 4; b++) if ((cd >> (22 + b)) & 1) if (anynz(cac[1][b], 15)) { cm |= H264B2_CM_CR(b); put16(cac[1][b], 16, 1); }
         }
         I.coef_mask = cm;
         if (m.cls == H264B2_MB_I4x4) { uint64_t v = 0; for (int b = 0; b < 16; b++) v |= (uint64_t)(m.ipred[b] & 15) << (4 * b); F.modes[cur] = v; }
