@@ -114,16 +114,15 @@ int Front::handle_slice_nal(int nal_ref_idc, int nal_unit_type) {
 
 void Front::start_picture_storage() {
     Slot &s = slots[cur];
-    mbs.assign(nmb, MbT());
-    memset(mbs.data(), 0, sizeof(MbT) * nmb);
-    info.assign(nmb, H264B2MbInfo()); memset(info.data(), 0, sizeof(H264B2MbInfo) * nmb);
+    mbs.resize(nmb); memset(mbs.data(), 0, sizeof(MbT) * nmb);
+    info.resize(nmb); memset(info.data(), 0, sizeof(H264B2MbInfo) * nmb);
     modes.assign(nmb, 0); coff.assign(nmb, 0);
     coefs.clear();
     weights.clear();
     H264B2Weight d; memset(&d, 0, sizeof d); for (int c = 0; c < 3; c++) { d.w0[c] = 1; d.w1[c] = 1; }
     weights.push_back(d);
-    s.motion.assign(nmb, H264B2MbMotion()); memset(s.motion.data(), 0, sizeof(H264B2MbMotion) * nmb);
-    s.col.assign(nmb, ColMb()); memset(s.col.data(), 0, sizeof(ColMb) * nmb);
+    s.motion.resize(nmb); memset(s.motion.data(), 0, sizeof(H264B2MbMotion) * nmb);
+    s.col.resize(nmb); memset(s.col.data(), 0, sizeof(ColMb) * nmb);
     s.decode_idx = decode_count++;
     has_inter = 0; pic_active = 1;
     mb_skip_flag = 0; mb_field = 0;          // CH264SliceData::init() at picture reset (SD:29-41)

@@ -123,13 +123,33 @@ int parse_slice_header(BitReader &br, int nal_ref_idc, int nal_unit_type, const 
 bool first_vcl_nal_of_picture(const SliceHeader &cur, const SliceHeader &last);
 
 // ------------------------------------------------------------------ CABAC arithmetic decoder (9.3.1.2, 9.3.3.2; H264Cabac.cpp:1041-1086, 2577-2824)
+extern const uint8_t (&g_range_lps)[64][4];
+extern const uint8_t (&g_trans_lps)[64];
+extern const uint8_t (&g_trans_mps)[64];
 struct Cabac {
     BitReader *br = nullptr;
     uint32_t range = 0, offset = 0;
     uint8_t state[1024];          // (pStateIdx << 1) | valMPS
     void init_contexts(int slice_type, int cabac_init_idc, int slice_qp);
     void init_engine(BitReader *b) { br = b; range = 510; offset = br->u(9); }
-    int decision(int ctx);
+    inline int decision(int ctx) {
+        const uint32_t s = state[ctx], p = s >> 1;
+        uint32_t mps = s & 1;
+        const uint32_t rlps = g_range_lps[p][(range >> 6) & 3];
+        int bin;
+        range -= rlps;
+        if (offset >= range) {
+            bin = (int)(mps ^ 1); offset -= range; range = rlps;
+            if (p == 0) mps ^= 1;
+            state[ctx] = (uint8_t)((g_trans_lps[p] << 1) | mps);
+            const int n = __builtin_clz(range) - 23; range <<= n; offset = (offset << n) | br->u(n);
+        } else {
+            bin = (int)mps;
+            state[ctx] = (uint8_t)((g_trans_mps[p] << 1) | mps);
+            if (range < 256) { range <<= 1; offset = (offset << 1) | br->u1(); }      // the MPS path needs at most one shift
+        }
+        return bin;
+    }
     inline int bypass() { offset = (offset << 1) | br->u1(); if (offset >= range) { offset -= range; return 1; } return 0; }
     inline int terminate() {
         range -= 2;

@@ -303,23 +303,9 @@ void Cabac::init_contexts(int slice_type, int cabac_init_idc, int slice_qp) {
     }
 }
 
-int Cabac::decision(int ctx) {
-    const uint32_t s = state[ctx], p = s >> 1;
-    uint32_t mps = s & 1;
-    const uint32_t rlps = kRangeTabLPS[p][(range >> 6) & 3];
-    int bin;
-    range -= rlps;
-    if (offset >= range) {
-        bin = (int)(mps ^ 1); offset -= range; range = rlps;
-        if (p == 0) mps ^= 1;
-        state[ctx] = (uint8_t)((kTransIdxLPS[p] << 1) | mps);
-    } else {
-        bin = (int)mps;
-        state[ctx] = (uint8_t)((kTransIdxMPS[p] << 1) | mps);
-    }
-    if (range < 256) { const int n = __builtin_clz(range) - 23; range <<= n; offset = (offset << n) | br->u(n); }
-    return bin;
-}
+const uint8_t (&g_range_lps)[64][4] = kRangeTabLPS;
+const uint8_t (&g_trans_lps)[64] = kTransIdxLPS;
+const uint8_t (&g_trans_mps)[64] = kTransIdxMPS;
 
 const uint16_t (*coeff_token_table())[17][4][2] { return kCoeffToken; }
 const uint16_t (*total_zeros_table())[16][16][2] { return kTotalZeros; }

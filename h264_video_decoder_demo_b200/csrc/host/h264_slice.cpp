@@ -772,10 +772,15 @@ struct Dec {
         else for (int k = 0; k < 2; k++) mvp[k] = A.mv[k] + B.mv[k] + C.mv[k] - std::min(A.mv[k], std::min(B.mv[k], C.mv[k])) - std::max(A.mv[k], std::max(B.mv[k], C.mv[k]));
     }
     // Reference_picture_selection_process (IP:2117-2197): slot + view of RefPicListX[refIdx]; -1 on failure
-    int select_ref(int list, int refIdx) const {
+    int list_ok[2] = {-1, -1};        // per slice: every entry of RefPicListX[0..len) is a marked frame (IP:2134-2147 checks this on every call)
+    int select_ref(int list, int refIdx) {
         if (refIdx < 0 || refIdx >= 32) return -1;
-        const int len = S.listlen[list];
-        for (int i = 0; i < len; i++) { const int s = S.list[list][i]; if (s < 0 || F.slots[s].p_coded_marked != 1) return -1; }
+        if (list_ok[list] < 0) {
+            list_ok[list] = 1;
+            const int len = S.listlen[list];
+            for (int i = 0; i < len; i++) { const int s = S.list[list][i]; if (s < 0 || F.slots[s].p_coded_marked != 1) { list_ok[list] = 0; break; } }
+        }
+        if (!list_ok[list]) return -1;
         if (!mbs[cur].field) { const int s = refIdx < 34 ? S.list[list][refIdx] : -1; return s < 0 ? -1 : (s << 2); }
         const int s = S.list[list][refIdx / 2];
         if (s < 0) return -1;
@@ -811,7 +816,16 @@ struct Dec {
         mvCol[0] = R.motion[addr].mv[l][b][0]; mvCol[1] = R.motion[addr].mv[l][b][1]; *refIdxCol = c.ref[l][q];
         return 0;
     }
+    std::vector<int32_t> wcache;       // per slice: (refIdxL0, refIdxL1, field MB parity) -> weight table index
     int weight_index(int ref0, int ref1, int pf0, int pf1) {
+        if (ref0 < -1 || ref0 > 31 || ref1 < -1 || ref1 > 31) return weight_index_slow(ref0, ref1, pf0, pf1);
+        if (wcache.empty()) wcache.assign(33 * 33 * 3, -1);
+        const int par = mbs[cur].field ? 1 + (cur & 1) : 0;
+        int32_t &c = wcache[((ref0 + 1) * 33 + (ref1 + 1)) * 3 + par];
+        if (c < 0) { const int v = weight_index_slow(ref0, ref1, pf0, pf1); if (v < 0) return v; c = v; }
+        return c;
+    }
+    int weight_index_slow(int ref0, int ref1, int pf0, int pf1) {
         // IP:538-546 + Derivation_process_for_prediction_weights (IP:2833-3047) + the mode selection of IP:2545-2610
         const int st = sh.slice_type % 5;
         int logWD[3] = {0, 0, 0}, w0[3] = {1, 1, 1}, w1[3] = {1, 1, 1}, o0[3] = {0, 0, 0}, o1[3] = {0, 0, 0};
@@ -880,8 +894,10 @@ struct Dec {
         return (int)F.weights.size() - 1;
     }
 
+    bool dc_valid = false; int dc_r[2], dc_zero, dc_mvp[2][2];
     int inter_prediction() {       // the derivation half of Inter_prediction_process (IP:412-667)
         MbT &m = mbs[cur];
+        dc_valid = false;
         H264B2MbMotion &M = mot[cur];
         memset(M.ref_surf, -1, sizeof M.ref_surf); memset(M.ref_ident, -1, sizeof M.ref_ident);
         F.has_inter = 1;
@@ -911,22 +927,28 @@ struct Dec {
                     refIdx[1] = -1;      // stays at its initial value in the reference
                 } else if (direct16 || subDirect) {
                     if (!sh.direct_spatial_mv_pred_flag) { F.error = "temporal direct prediction is not supported"; return -2; }
-                    // spatial direct (IP:1302-1428): neighbours of the whole macroblock, as partition 0 of width 16
-                    int r[2];
-                    for (int l = 0; l < 2; l++) {
-                        NbMv A, B, C; neighbours(0, 0, 16, l, A, B, C);
-                        auto minpos = [](int a, int b) { return (a >= 0 && b >= 0) ? std::min(a, b) : std::max(a, b); };
-                        r[l] = minpos(A.ref, minpos(B.ref, C.ref));
+                    // spatial direct (IP:1302-1428): neighbours of the whole macroblock, as partition 0 of width 16.  They lie outside
+                    // the macroblock, so the reference indices and the two predictors are the same for all of its direct 4x4 blocks.
+                    if (!dc_valid) {
+                        for (int l = 0; l < 2; l++) {
+                            NbMv A, B, C; neighbours(0, 0, 16, l, A, B, C);
+                            auto minpos = [](int a, int b) { return (a >= 0 && b >= 0) ? std::min(a, b) : std::max(a, b); };
+                            dc_r[l] = minpos(A.ref, minpos(B.ref, C.ref));
+                        }
+                        dc_zero = 0;
+                        if (dc_r[0] < 0 && dc_r[1] < 0) { dc_r[0] = dc_r[1] = 0; dc_zero = 1; }
+                        for (int l = 0; l < 2; l++) { dc_mvp[l][0] = dc_mvp[l][1] = 0; if (!dc_zero && dc_r[l] >= 0) predict_mv(m, 0, 0, 0, 16, l, dc_r[l], dc_mvp[l]); }
+                        dc_valid = true;
                     }
-                    int directZero = 0;
-                    if (r[0] < 0 && r[1] < 0) { r[0] = r[1] = 0; directZero = 1; }
+                    int r[2] = {dc_r[0], dc_r[1]};
+                    const int directZero = dc_zero;
                     int addrCol = 0, mvCol[2] = {0, 0}, refCol = 0;
                     if (colocated(p, s, &addrCol, mvCol, &refCol)) return -1;
                     const int l10 = S.list[1][0];
                     // REF Q10: no frame/field unit conversion of mvCol
                     const int colZero = (F.slots[l10].p_mark == MARK_SHORT && refCol == 0 && mvCol[0] >= -1 && mvCol[0] <= 1 && mvCol[1] >= -1 && mvCol[1] <= 1) ? 1 : 0;
-                    if (directZero || r[0] < 0 || (r[0] == 0 && colZero)) mvL0[0] = mvL0[1] = 0; else predict_mv(m, 0, 0, 0, 16, 0, r[0], mvL0);
-                    if (directZero || r[1] < 0 || (r[1] == 0 && colZero)) mvL1[0] = mvL1[1] = 0; else predict_mv(m, 0, 0, 0, 16, 1, r[1], mvL1);
+                    if (directZero || r[0] < 0 || (r[0] == 0 && colZero)) mvL0[0] = mvL0[1] = 0; else { mvL0[0] = dc_mvp[0][0]; mvL0[1] = dc_mvp[0][1]; }
+                    if (directZero || r[1] < 0 || (r[1] == 0 && colZero)) mvL1[0] = mvL1[1] = 0; else { mvL1[0] = dc_mvp[1][0]; mvL1[1] = dc_mvp[1][1]; }
                     refIdx[0] = r[0]; refIdx[1] = r[1];
                     pf[0] = r[0] >= 0; pf[1] = r[1] >= 0;
                 } else {
