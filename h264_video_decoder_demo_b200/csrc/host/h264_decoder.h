@@ -70,6 +70,7 @@ struct Front {
     std::string error;
     // stream
     std::vector<uint8_t> file; const uint8_t *data = nullptr; size_t size = 0, nal_pos = 0;
+    size_t range_begin = 0; int more_follows = 0, primed = 1;      // closed-GOP shard decoding (h264b2_front_open_range)
     std::vector<uint8_t> rbsp;
     SPS spss[32]; PPS ppss[256];
     int sps_seen = 0, pps_seen = 0, max_num_reorder_frames = 0;

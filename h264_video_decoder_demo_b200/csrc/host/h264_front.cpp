@@ -38,6 +38,28 @@ static bool find_start(const uint8_t *d, size_t n, size_t from, size_t *pos, int
 }
 
 int Front::pump() {
+    if (!primed) {          // a GOP shard: take the parameter sets in front of it first
+        primed = 1;
+        size_t pos = 0, p1; int l1;
+        while (find_start(data, range_begin, pos, &p1, &l1)) {
+            const size_t start = p1 + l1; size_t p2; int l2; size_t end = range_begin;
+            if (find_start(data, range_begin, start, &p2, &l2)) end = p2;
+            pos = end;
+            if (end <= start) continue;
+            const int t = data[start] & 31;
+            if (t != 7 && t != 8) continue;
+            rbsp.clear();
+            for (size_t i = 1; i < end - start; i++) {
+                const uint8_t *nal = data + start; const size_t n = end - start;
+                if (i + 2 < n && nal[i] == 0 && nal[i + 1] == 0 && nal[i + 2] == 3) { rbsp.push_back(0); rbsp.push_back(0); i += 2; } else rbsp.push_back(nal[i]);
+            }
+            if (!rbsp.empty()) rbsp.back() &= 0xFE;
+            const size_t nbytes = rbsp.size(); rbsp.resize(nbytes + 16, 0); br.init(rbsp.data(), nbytes);
+            if (t == 7) { SPS sp; parse_sps(br, sp); if (sp.sps_id >= 0 && sp.sps_id < 32) { spss[sp.sps_id] = sp; max_num_reorder_frames = sp.max_num_reorder_frames; sps_seen = 1; } }
+            else { PPS pp; if (parse_pps(br, pp, spss) != -2 && pp.pps_id >= 0 && pp.pps_id < 256) { ppss[pp.pps_id] = pp; pps_seen = 1; } }
+        }
+        nal_pos = range_begin;
+    }
     // Decode NAL units until at least one event is queued.
     while (events.size() == ev_pos) {
         events.clear(); ev_pos = 0;
@@ -47,7 +69,7 @@ int Front::pump() {
             // end of stream: H264VideoDecoder.cpp:354-374 — the current picture goes to the output process WITHOUT the
             // deblocking/marking of end_decode_the_picture (Q1), then everything pending is flushed.
             if (!stop) {
-                if (cur >= 0) { if (pic_active) emit_picture(0); do_callback(cur, slots[cur].decode_idx >= 0 ? pic_sh.IdrPicFlag : 0); }
+                if (cur >= 0) { if (pic_active) emit_picture(more_follows ? 1 : 0); do_callback(cur, slots[cur].decode_idx >= 0 ? pic_sh.IdrPicFlag : 0); }
                 do_callback(-1, 1);
             }
             eof_done = 1;
@@ -501,6 +523,30 @@ extern "C" int h264b2_front_open_memory(H264B2Front *f, const uint8_t *data, siz
     f->f.data = data; f->f.size = bytes; f->f.nal_pos = 0;
     return 0;
 }
+extern "C" int h264b2_front_gop_offsets(const uint8_t *data, size_t bytes, size_t *offsets, int max_gops) {
+    if (!data) return -1;
+    int n = 0;
+    size_t pos = 0, p1, group = 0; int l1; bool in_group = false;
+    while (find_start(data, bytes, pos, &p1, &l1)) {
+        const size_t start = p1 + l1;
+        pos = start;
+        if (start >= bytes) break;
+        const int t = data[start] & 31;
+        if (t >= 6 && t <= 9) { if (!in_group) { group = p1; in_group = true; } continue; }       // SEI / SPS / PPS / AUD in front of a picture
+        if (t == 5 && start + 1 < bytes && (data[start + 1] & 0x80)) {                                // IDR slice with first_mb_in_slice == 0
+            const size_t off = n == 0 ? 0 : (in_group ? group : p1);
+            if (offsets && n < max_gops) offsets[n] = off;
+            n++;
+        }
+        in_group = false;
+    }
+    return n;
+}
+extern "C" int h264b2_front_open_range(H264B2Front *f, const uint8_t *data, size_t bytes, size_t begin, size_t end, int more_follows) {
+    if (!f || !data || begin > end || end > bytes) return -1;
+    f->f.data = data; f->f.size = end; f->f.nal_pos = begin; f->f.range_begin = begin; f->f.more_follows = more_follows; f->f.primed = begin == 0;
+    return 0;
+}
 extern "C" int h264b2_front_open_file(H264B2Front *f, const char *path) {
     if (!f || !path) return -1;
     FILE *fp = fopen(path, "rb");
@@ -516,11 +562,15 @@ extern "C" int h264b2_front_release(H264B2Front *f, void *block) { if (!f) retur
 extern "C" const char *h264b2_front_last_error(H264B2Front *f) { return f ? f->f.error.c_str() : "null front end"; }
 
 extern "C" int h264b2_front_write_container(const char *h264_path, const char *container_path, int max_pictures) {
+    return h264b2_front_write_container_range(h264_path, container_path, max_pictures, 0, 0, 0);
+}
+extern "C" int h264b2_front_write_container_range(const char *h264_path, const char *container_path, int max_pictures, size_t begin, size_t end, int more_follows) {
     struct FileHdr { char magic[8]; uint32_t version, width_mbs, height_mbs, n_pics, n_out, hdr_bytes, pichdr_bytes, reserved; } fh;
     struct OutRec { int32_t decode_idx, pad; uint64_t sum; };
     H264B2Front *f = nullptr;
     if (h264b2_front_create(&f, nullptr, nullptr, nullptr)) return -1;
     if (h264b2_front_open_file(f, h264_path)) { fprintf(stderr, "%s\n", h264b2_front_last_error(f)); h264b2_front_destroy(f); return -1; }
+    if (end > begin && h264b2_front_open_range(f, f->f.data, f->f.size, begin, end, more_follows)) { h264b2_front_destroy(f); return -1; }
     FILE *fo = fopen(container_path, "wb");
     if (!fo) { h264b2_front_destroy(f); return -1; }
     memset(&fh, 0, sizeof fh);

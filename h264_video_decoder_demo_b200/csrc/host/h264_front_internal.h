@@ -36,8 +36,8 @@ struct BitReader {
     }
     inline uint32_t peek(int k) const {          // k in [1, 32]
         if (pos + k > nbits) return peek_slow(k);
-        const uint8_t *p = d + (pos >> 3);
-        uint64_t v = ((uint64_t)p[0] << 56) | ((uint64_t)p[1] << 48) | ((uint64_t)p[2] << 40) | ((uint64_t)p[3] << 32) | ((uint64_t)p[4] << 24) | ((uint64_t)p[5] << 16) | ((uint64_t)p[6] << 8) | p[7];
+        uint64_t v; memcpy(&v, d + (pos >> 3), 8);          // the buffer is padded, see Front::pump
+        v = __builtin_bswap64(v);
         return (uint32_t)((v << (pos & 7)) >> (64 - k));
     }
     inline void skip(int k) { pos += k; }
@@ -124,8 +124,7 @@ bool first_vcl_nal_of_picture(const SliceHeader &cur, const SliceHeader &last);
 
 // ------------------------------------------------------------------ CABAC arithmetic decoder (9.3.1.2, 9.3.3.2; H264Cabac.cpp:1041-1086, 2577-2824)
 extern const uint8_t (&g_range_lps)[64][4];
-extern const uint8_t (&g_trans_lps)[64];
-extern const uint8_t (&g_trans_mps)[64];
+extern uint8_t g_next_state[2][128];      // [0 = MPS decoded, 1 = LPS decoded][(pStateIdx << 1) | valMPS]  (Table 9-45 on the packed state)
 struct Cabac {
     BitReader *br = nullptr;
     uint32_t range = 0, offset = 0;
@@ -133,22 +132,18 @@ struct Cabac {
     void init_contexts(int slice_type, int cabac_init_idc, int slice_qp);
     void init_engine(BitReader *b) { br = b; range = 510; offset = br->u(9); }
     inline int decision(int ctx) {
-        const uint32_t s = state[ctx], p = s >> 1;
-        uint32_t mps = s & 1;
-        const uint32_t rlps = g_range_lps[p][(range >> 6) & 3];
-        int bin;
+        const uint32_t s = state[ctx];
+        const uint32_t rlps = g_range_lps[s >> 1][(range >> 6) & 3];
         range -= rlps;
-        if (offset >= range) {
-            bin = (int)(mps ^ 1); offset -= range; range = rlps;
-            if (p == 0) mps ^= 1;
-            state[ctx] = (uint8_t)((g_trans_lps[p] << 1) | mps);
-            const int n = __builtin_clz(range) - 23; range <<= n; offset = (offset << n) | br->u(n);
-        } else {
-            bin = (int)mps;
-            state[ctx] = (uint8_t)((g_trans_mps[p] << 1) | mps);
+        if (offset < range) {
+            state[ctx] = g_next_state[0][s];
             if (range < 256) { range <<= 1; offset = (offset << 1) | br->u1(); }      // the MPS path needs at most one shift
+            return (int)(s & 1);
         }
-        return bin;
+        offset -= range; range = rlps;
+        state[ctx] = g_next_state[1][s];
+        const int n = __builtin_clz(range) - 23; range <<= n; offset = (offset << n) | br->u(n);
+        return (int)((s & 1) ^ 1);
     }
     inline int bypass() { offset = (offset << 1) | br->u1(); if (offset >= range) { offset -= range; return 1; } return 0; }
     inline int terminate() {

@@ -17,7 +17,9 @@ struct Pin { H264B2Context *ctx; };
 void *pin_alloc(void *u, size_t n) { void *p = nullptr; return h264b2_host_alloc(((Pin *)u)->ctx, n, &p) == 0 ? p : nullptr; }
 void pin_free(void *u, void *p) { h264b2_host_free(((Pin *)u)->ctx, p); }
 
-struct Stream {
+struct Stream {                 // one decoding unit: a whole stream, or one closed-GOP shard of it
+    int owner = 0; size_t begin = 0, end = 0; int more_follows = 0;
+    std::vector<uint64_t> sums;
     H264B2Front *fe = nullptr;
     std::deque<H264B2FrontEvent> q;
     int pics_queued = 0;
@@ -28,10 +30,39 @@ struct Stream {
 enum { QUEUE_DEPTH = 3, RING = 4 };
 }
 
-extern "C" int h264b2_multi_decode(int device, int n_streams, const char *const *paths, int n_threads, int readback,
+extern "C" int h264b2_multi_decode(int device, int n_inputs, const char *const *paths, int n_threads, int flags,
                                    uint64_t *stream_hash, H264B2MultiStats *stats, char *err, size_t err_len) {
     auto fail = [&](int code, const std::string &m) { if (err && err_len) snprintf(err, err_len, "%s", m.c_str()); return code; };
-    if (n_streams <= 0 || !paths || n_threads <= 0) return fail(-1, "bad argument");
+    if (n_inputs <= 0 || !paths || n_threads <= 0) return fail(-1, "bad argument");
+    const int readback = flags & H264B2_MULTI_READBACK, split = flags & H264B2_MULTI_SPLIT_GOPS;
+    // the byte streams (identical paths share one buffer), and the decoding units: whole streams or closed-GOP shards
+    std::vector<std::vector<uint8_t>> bufs; std::vector<std::string> names; std::vector<int> buf_of(n_inputs);
+    for (int i = 0; i < n_inputs; i++) {
+        int b = -1;
+        for (size_t k = 0; k < names.size(); k++) if (names[k] == paths[i]) b = (int)k;
+        if (b < 0) {
+            FILE *fp = fopen(paths[i], "rb");
+            if (!fp) return fail(-1, std::string("cannot open ") + paths[i]);
+            fseek(fp, 0, SEEK_END); const long n = ftell(fp); fseek(fp, 0, SEEK_SET);
+            std::vector<uint8_t> v((size_t)n + 16, 0);
+            if (n > 0 && fread(v.data(), 1, (size_t)n, fp) != (size_t)n) { fclose(fp); return fail(-1, std::string("short read: ") + paths[i]); }
+            fclose(fp);
+            v.resize((size_t)n);
+            bufs.push_back(std::move(v)); names.push_back(paths[i]); b = (int)bufs.size() - 1;
+        }
+        buf_of[i] = b;
+    }
+    std::vector<Stream> st;
+    for (int i = 0; i < n_inputs; i++) {
+        const std::vector<uint8_t> &v = bufs[buf_of[i]];
+        std::vector<size_t> offs(1, 0);
+        if (split) { const int n = h264b2_front_gop_offsets(v.data(), v.size(), nullptr, 0); if (n > 1) { offs.assign((size_t)n, 0); h264b2_front_gop_offsets(v.data(), v.size(), offs.data(), n); } }
+        for (size_t g = 0; g < offs.size(); g++) {
+            Stream x; x.owner = i; x.begin = offs[g]; x.end = g + 1 < offs.size() ? offs[g + 1] : v.size(); x.more_follows = g + 1 < offs.size();
+            st.push_back(std::move(x));
+        }
+    }
+    const int n_streams = (int)st.size();
     if (n_threads > n_streams) n_threads = n_streams;
     // picture size from the first stream (all streams of one context share it)
     int wmb = 0, hmb = 0;
@@ -51,12 +82,13 @@ extern "C" int h264b2_multi_decode(int device, int n_streams, const char *const 
     const size_t frame_bytes = (size_t)wmb * hmb * 384;
     uint8_t *frames = nullptr;
     if (readback && h264b2_host_alloc(ctx, frame_bytes * n_streams * RING, (void **)&frames)) { std::string m = h264b2_last_error(); h264b2_destroy(ctx); return fail(-3, m); }
-    std::vector<Stream> st(n_streams);
     std::string first_error;
-    for (int s = 0; s < n_streams; s++)
-        if (h264b2_front_create(&st[s].fe, pin_alloc, pin_free, &pin) || h264b2_front_open_file(st[s].fe, paths[s])) { first_error = st[s].fe ? h264b2_front_last_error(st[s].fe) : "out of memory"; break; }
+    for (int s = 0; s < n_streams; s++) {
+        const std::vector<uint8_t> &v = bufs[buf_of[st[s].owner]];
+        if (h264b2_front_create(&st[s].fe, pin_alloc, pin_free, &pin) || h264b2_front_open_range(st[s].fe, v.data(), v.size(), st[s].begin, st[s].end, st[s].more_follows)) { first_error = st[s].fe ? h264b2_front_last_error(st[s].fe) : "out of memory"; break; }
+    }
     H264B2MultiStats S; memset(&S, 0, sizeof S);
-    S.threads = n_threads; S.streams = n_streams; S.width_mbs = wmb; S.height_mbs = hmb;
+    S.threads = n_threads; S.streams = n_inputs; S.units = n_streams; S.width_mbs = wmb; S.height_mbs = hmb;
     int rc = 0;
     if (first_error.empty()) {
         std::mutex mu; std::condition_variable cv_space, cv_data;
@@ -76,7 +108,7 @@ extern "C" int h264b2_multi_decode(int device, int n_streams, const char *const 
                         const int r = h264b2_front_next(x.fe, &ev);
                         busy[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
                         std::lock_guard<std::mutex> l(mu);
-                        if (r < 0) { if (first_error.empty()) first_error = std::string(paths[s]) + ": " + h264b2_front_last_error(x.fe); memset(&ev, 0, sizeof ev); ev.kind = H264B2_EV_END; }
+                        if (r < 0) { if (first_error.empty()) first_error = std::string(paths[x.owner]) + ": " + h264b2_front_last_error(x.fe); memset(&ev, 0, sizeof ev); ev.kind = H264B2_EV_END; }
                         x.q.push_back(ev);
                         if (ev.kind == H264B2_EV_PICTURE) x.pics_queued++;
                         if (ev.kind == H264B2_EV_END) x.parsed_all = true;
@@ -116,7 +148,7 @@ extern "C" int h264b2_multi_decode(int device, int n_streams, const char *const 
                 if (stream_hash) {
                     sums.assign(round.size(), 0);
                     if (h264b2_checksum_pictures(ctx, (int)round.size(), sids.data(), surfs.data(), sums.data())) { rc = -3; first_error = h264b2_last_error(); break; }
-                    for (size_t i = 0; i < round.size(); i++) st[round[i].first].hash = st[round[i].first].hash * 0x100000001B3ULL + sums[i];
+                    for (size_t i = 0; i < round.size(); i++) st[round[i].first].sums.push_back(sums[i]);
                 }
                 if (readback) {
                     bool wrap = false;
@@ -149,7 +181,10 @@ extern "C" int h264b2_multi_decode(int device, int n_streams, const char *const 
         for (double b : busy) S.parse_seconds += b;
         if (!first_error.empty() && rc == 0) rc = -1;
     } else rc = -1;
-    if (stream_hash) for (int s = 0; s < n_streams; s++) stream_hash[s] = st[s].hash;
+    if (stream_hash) {          // per input stream: chain over its output frames, GOP shards in stream order
+        for (int i = 0; i < n_inputs; i++) stream_hash[i] = 0;
+        for (auto &x : st) for (uint64_t v : x.sums) stream_hash[x.owner] = stream_hash[x.owner] * 0x100000001B3ULL + v;
+    }
     for (auto &x : st) if (x.fe) h264b2_front_destroy(x.fe);
     if (frames) h264b2_host_free(ctx, frames);
     h264b2_destroy(ctx);

@@ -304,8 +304,15 @@ void Cabac::init_contexts(int slice_type, int cabac_init_idc, int slice_qp) {
 }
 
 const uint8_t (&g_range_lps)[64][4] = kRangeTabLPS;
-const uint8_t (&g_trans_lps)[64] = kTransIdxLPS;
-const uint8_t (&g_trans_mps)[64] = kTransIdxMPS;
+uint8_t g_next_state[2][128];
+static const bool g_next_state_init = [] {
+    for (int s = 0; s < 128; s++) {
+        const int p = s >> 1, mps = s & 1;
+        g_next_state[0][s] = (uint8_t)((kTransIdxMPS[p] << 1) | mps);
+        g_next_state[1][s] = (uint8_t)((kTransIdxLPS[p] << 1) | (p == 0 ? mps ^ 1 : mps));
+    }
+    return true;
+}();
 
 const uint16_t (*coeff_token_table())[17][4][2] { return kCoeffToken; }
 const uint16_t (*total_zeros_table())[16][16][2] { return kTotalZeros; }

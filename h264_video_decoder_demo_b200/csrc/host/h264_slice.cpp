@@ -350,33 +350,37 @@ struct Dec {
         int sigBase, lastBase, absBase;
         if (cat == CAT_LUMA8) { sigBase = fld ? 436 : 402; lastBase = fld ? 451 : 417; absBase = 426; }
         else { sigBase = (fld ? 277 : 105) + sigOff[cat]; lastBase = (fld ? 338 : 166) + sigOff[cat]; absBase = 227 + absOff[cat]; }
-        uint8_t sig[64]; memset(sig, 0, sizeof sig);
-        int numCoeff = endIdx + 1, i = startIdx;
+        static const uint8_t ident[64] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41,
+                                          42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63};
+        static const uint8_t cdcInc[4] = {0, 1, 2, 2};
+        const uint8_t *sigInc = cat == CAT_LUMA8 ? (fld ? kSig8Field : kSig8Frame) : cat == CAT_CDC ? cdcInc : ident;
+        const uint8_t *lastInc = cat == CAT_LUMA8 ? kLast8 : cat == CAT_CDC ? cdcInc : ident;
+        uint8_t where[64];            // positions of the significant coefficients, in scan order
+        int nsig = 0, numCoeff = endIdx + 1, i = startIdx;
         while (i < numCoeff - 1) {
-            int si, li;
-            if (cat == CAT_LUMA8) { si = fld ? kSig8Field[i] : kSig8Frame[i]; li = kLast8[i]; }
-            else if (cat == CAT_CDC) { si = li = std::min(i, 2); }
-            else si = li = i;
-            sig[i] = (uint8_t)cb.decision(sigBase + si);
-            if (sig[i] && cb.decision(lastBase + li)) numCoeff = i + 1;
+            if (cb.decision(sigBase + sigInc[i])) {
+                where[nsig++] = (uint8_t)i;
+                if (cb.decision(lastBase + lastInc[i])) { numCoeff = i + 1; break; }
+            }
             i++;
         }
-        int eq1 = 0, gt1 = 0, total = 0;
-        auto level = [&]() {
+        if (nsig == 0 || where[nsig - 1] != numCoeff - 1) where[nsig++] = (uint8_t)(numCoeff - 1);     // the last position is significant by inference
+        int eq1 = 0, gt1 = 0;
+        const int gtMax = 4 - (cat == CAT_CDC ? 1 : 0);
+        for (int k = nsig - 1; k >= 0; k--) {
             int ctx = absBase + (gt1 != 0 ? 0 : std::min(4, 1 + eq1));
             int v = 0;
             if (cb.decision(ctx)) {
-                ctx = absBase + 5 + std::min(4 - (cat == CAT_CDC ? 1 : 0), gt1);
+                ctx = absBase + 5 + std::min(gtMax, gt1);
                 v = 1;
                 while (v < 14 && cb.decision(ctx)) v++;
-                if (v >= 14) { int k = 0; while (cb.bypass()) { v += 1 << k; k++; if (k > 24) break; } while (k--) v += cb.bypass() << k; }
+                if (v >= 14) { int e = 0; while (cb.bypass()) { v += 1 << e; e++; if (e > 24) break; } while (e--) v += cb.bypass() << e; }
             }
             const int a = v + 1;
             if (a == 1) eq1++; else gt1++;
-            return cb.bypass() ? -a : a;
-        };
-        lvl[numCoeff - 1] = level(); total = 1;
-        for (i = numCoeff - 2; i >= startIdx; i--) if (sig[i]) { lvl[i] = level(); total++; }
+            lvl[where[k]] = cb.bypass() ? -a : a;
+        }
+        const int total = nsig;
         if (cat == CAT_I16DC || cat == CAT_CDC) m.cbf_dc ^= (uint8_t)(1 << (comp + 1));
         else m.cbf_ac[comp + 1] ^= (uint16_t)(1 << blk);
         return total;

@@ -55,6 +55,13 @@ int h264b2_front_destroy(H264B2Front *f);
 /* Annex-B byte stream, whole file (the reference also reads whole NAL units from a file buffer). The memory must stay valid. */
 int h264b2_front_open_memory(H264B2Front *f, const uint8_t *data, size_t bytes);
 int h264b2_front_open_file(H264B2Front *f, const char *path);
+/* Closed-GOP sharding: byte offsets at which a closed GOP starts, i.e. the first parameter-set/SEI NAL in
+ * front of every IDR picture (offset 0 for the first).  Returns the number of GOPs found (<= max_gops written). */
+int h264b2_front_gop_offsets(const uint8_t *data, size_t bytes, size_t *offsets, int max_gops);
+/* Decode only [begin, end) of the stream — one or more whole closed GOPs.  Parameter sets that precede `begin` are
+ * parsed first.  more_follows = 1: the last picture of the range is completed the way the reference completes a picture that
+ * is followed by another one (deblocked, H264PictureBase.cpp:707) instead of as the stream's tail picture (Q1). */
+int h264b2_front_open_range(H264B2Front *f, const uint8_t *data, size_t bytes, size_t begin, size_t end, int more_follows);
 /* Pull the next event. Returns 0, or <0 on a fatal stream error (message in h264b2_front_last_error). */
 int h264b2_front_next(H264B2Front *f, H264B2FrontEvent *ev);
 /* Give a picture block back for reuse (blocks still out at destroy time are freed there). */
@@ -62,6 +69,8 @@ int h264b2_front_release(H264B2Front *f, void *block);
 const char *h264b2_front_last_error(H264B2Front *f);
 /* Convenience for tools/tests: parse a whole stream into a picture container file (same format the reference harness writes). */
 int h264b2_front_write_container(const char *h264_path, const char *container_path, int max_pictures);
+/* Same for the byte range [begin, end) of the file (a closed-GOP shard, see h264b2_front_open_range); end == 0: whole file. */
+int h264b2_front_write_container_range(const char *h264_path, const char *container_path, int max_pictures, size_t begin, size_t end, int more_follows);
 
 #ifdef __cplusplus
 }

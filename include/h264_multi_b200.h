@@ -21,14 +21,18 @@ typedef struct H264B2MultiStats {
     int64_t h2d_bytes;          /* structure-of-arrays bytes handed to h264b2_submit */
     int64_t d2h_bytes;          /* picture bytes copied back to page-locked host memory */
     int32_t threads, streams, submits, width_mbs, height_mbs;
+    int32_t units;              /* decoding units = streams, or closed-GOP shards with H264B2_MULTI_SPLIT_GOPS */
+    int32_t reserved;
 } H264B2MultiStats;
 
-/* readback: 0 = pictures stay on the GPU (only 64-bit checksums leave it when stream_hash != NULL), 1 = every output picture is
- *           copied to page-locked host memory (what an output callback receives).
+enum { H264B2_MULTI_READBACK = 1,     /* copy every output picture to page-locked host memory (what an output callback receives) */
+       H264B2_MULTI_SPLIT_GOPS = 2 }; /* decode the closed GOPs of every stream as independent units (own DPB each), SURVEY 8(e) */
+
+/* flags: H264B2_MULTI_*; without READBACK pictures stay on the GPU (only 64-bit checksums leave it when stream_hash != NULL).
  * stream_hash[n_streams] (optional): per stream, h = h * 0x100000001B3 + checksum(frame) over its output frames in output order
  *           (checksums computed on the GPU; the same chain oracle/ref_harness prints as stream_hash).
  * Returns 0, or <0 with a message in err. */
-int h264b2_multi_decode(int device, int n_streams, const char *const *paths, int n_threads, int readback,
+int h264b2_multi_decode(int device, int n_streams, const char *const *paths, int n_threads, int flags,
                         uint64_t *stream_hash, H264B2MultiStats *stats, char *err, size_t err_len);
 
 #ifdef __cplusplus

@@ -84,3 +84,35 @@ def test_front_end_error_behaviour(tmp_path):
     ref = replay.load_replay(rp)
     assert 1 <= len(got.pictures) <= len(ref.pictures) + 1
     assert got.pictures[0].mb_info.tobytes() == ref.pictures[0].mb_info.tobytes()
+
+
+def test_closed_gop_shards_parse_like_the_full_stream(tmp_path):
+    """a closed GOP parsed on its own (parameter sets taken from in front of it, last picture completed as
+    "another picture follows") yields the same macroblock data as the full-stream parse; only DPB slot numbers may differ."""
+    import numpy as np
+    from h264_video_decoder_demo_b200 import frontend, replay
+    name = "HeavyHand_1080p.B_frames.cabac"
+    src, ref_path = os.path.join(STREAM_DIR, name + ".h264"), os.path.join(FULL_DIR, name + ".bin.xz")
+    if not (os.path.exists(src) and os.path.exists(ref_path)):
+        pytest.skip("bundled streams / full reference containers not built")
+    data = open(src, "rb").read()
+    offs = frontend.gop_offsets(data)
+    assert offs == [0, 2506064]                      # SURVEY 8(e): the second SPS of the stream
+    ref = replay.load_replay(ref_path)
+    first = 0
+    for g, begin in enumerate(offs):
+        end = offs[g + 1] if g + 1 < len(offs) else len(data)
+        out = str(tmp_path / f"gop{g}.bin")
+        assert frontend.parse_to_container(src, out, 0, begin, end, more_follows=g + 1 < len(offs)) == 0
+        shard = replay.load_replay(out)
+        for k, a in enumerate(shard.pictures):
+            b = ref.pictures[first + k]
+            assert a.deblock_enable == b.deblock_enable and a.poc == b.poc and a.slice_type == b.slice_type
+            assert a.mb_info.tobytes() == b.mb_info.tobytes() and np.array_equal(a.coefs, b.coefs) and np.array_equal(a.intra_modes, b.intra_modes)
+            if b.motion is not None:
+                assert np.array_equal(a.motion["mv"], b.motion["mv"]) and np.array_equal(a.motion["wt_idx"], b.motion["wt_idx"])
+                assert np.array_equal(a.motion["ref_surf"] < 0, b.motion["ref_surf"] < 0)
+            assert a.weights.tobytes() == b.weights.tobytes()
+        assert [i + first for i in shard.out_order] == ref.out_order[first:first + len(shard.pictures)]
+        first += len(shard.pictures)
+    assert first == len(ref.pictures)
