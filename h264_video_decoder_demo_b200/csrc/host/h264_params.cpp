@@ -111,7 +111,9 @@ int parse_pps(BitReader &br, PPS &p, const SPS *spss) {
                 p.pic_scaling_list_present_flag[i] = br.u1();
                 if (p.pic_scaling_list_present_flag[i]) { if (i < 6) scaling_list(br, p.ScalingList4x4[i], 16, p.UseDefault4x4[i]); else scaling_list(br, p.ScalingList8x8[i - 6], 64, p.UseDefault8x8[i - 6]); }
             }
-        p.second_chroma_qp_index_offset = br.se();
+        // REF: second_chroma_qp_index_offset is only read inside the pic_scaling_matrix_present_flag block (H264PPS.cpp:207-226);
+        // without a PPS scaling matrix it keeps the value of chroma_qp_index_offset whatever the stream says
+        if (p.pic_scaling_matrix_present_flag) p.second_chroma_qp_index_offset = br.se();
     }
     p.valid = 1;
     return 0;

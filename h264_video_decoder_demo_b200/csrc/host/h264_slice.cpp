@@ -558,7 +558,7 @@ struct Dec {
     void classify_intra(MbT &m, int t) {       // I-slice mb_type 0..25
         memset(m.part_pm, 0, 4); m.num_part = 0; m.pm0_inter = 0;
         if (t == 0) { m.type = T_I_NxN; m.intra = 1; m.cls = m.t8x8 ? H264B2_MB_I8x8 : H264B2_MB_I4x4; }
-        else if (t == 25) { m.type = T_IPCM; m.intra = 0; m.ipcm = 1; m.cls = H264B2_MB_IPCM; }    // REF Q11: Intra_NA is not "intra"
+        else if (t == 25) { m.type = T_IPCM; m.intra = 0; m.ipcm = 1; m.cls = H264B2_MB_IPCM; m.i16mode = 3; }    // REF Q11: Intra_NA is not "intra"; Intra16x16PredMode = NA (-1) & 3
         else { m.type = T_I16; m.intra = 1; m.cls = H264B2_MB_I16x16; m.i16mode = (uint8_t)((t - 1) % 4); m.cbp_chroma = (uint8_t)(((t - 1) / 4) % 3); m.cbp_luma = (t - 1) >= 12 ? 15 : 0; }
     }
     // geometry of partition p / sub-partition s of the current macroblock

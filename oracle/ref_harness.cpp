@@ -61,6 +61,28 @@ static std::vector<OutRec> g_out;
 static uint64_t g_stream_hash = 0;
 static int g_wmb = 0, g_hmb = 0;
 static long g_dump_pix_idx = -1;
+// every slice's header, in the order slice_data() numbered them: the picture object only keeps the LAST slice's header, but
+// weights / slice type are per slice (multi-slice pictures with explicit weighted prediction)
+struct WHdr {   // the per-slice fields the weight derivation reads (plain copies: CH264SliceHeader owns malloc'ed maps)
+    int32_t slice_type, luma_log2_weight_denom, chroma_log2_weight_denom;
+    int32_t luma_weight_l0[32], luma_offset_l0[32], chroma_weight_l0[32][2], chroma_offset_l0[32][2];
+    int32_t luma_weight_l1[32], luma_offset_l1[32], chroma_weight_l1[32][2], chroma_offset_l1[32][2];
+    void load(const CH264SliceHeader &h) {
+        slice_type = h.slice_type; luma_log2_weight_denom = h.luma_log2_weight_denom; chroma_log2_weight_denom = h.chroma_log2_weight_denom;
+        memcpy(luma_weight_l0, h.luma_weight_l0, sizeof luma_weight_l0); memcpy(luma_offset_l0, h.luma_offset_l0, sizeof luma_offset_l0);
+        memcpy(chroma_weight_l0, h.chroma_weight_l0, sizeof chroma_weight_l0); memcpy(chroma_offset_l0, h.chroma_offset_l0, sizeof chroma_offset_l0);
+        memcpy(luma_weight_l1, h.luma_weight_l1, sizeof luma_weight_l1); memcpy(luma_offset_l1, h.luma_offset_l1, sizeof luma_offset_l1);
+        memcpy(chroma_weight_l1, h.chroma_weight_l1, sizeof chroma_weight_l1); memcpy(chroma_offset_l1, h.chroma_offset_l1, sizeof chroma_offset_l1);
+    }
+    void store(CH264SliceHeader &h) const {
+        h.slice_type = slice_type; h.luma_log2_weight_denom = luma_log2_weight_denom; h.chroma_log2_weight_denom = chroma_log2_weight_denom;
+        memcpy(h.luma_weight_l0, luma_weight_l0, sizeof luma_weight_l0); memcpy(h.luma_offset_l0, luma_offset_l0, sizeof luma_offset_l0);
+        memcpy(h.chroma_weight_l0, chroma_weight_l0, sizeof chroma_weight_l0); memcpy(h.chroma_offset_l0, chroma_offset_l0, sizeof chroma_offset_l0);
+        memcpy(h.luma_weight_l1, luma_weight_l1, sizeof luma_weight_l1); memcpy(h.luma_offset_l1, luma_offset_l1, sizeof luma_offset_l1);
+        memcpy(h.chroma_weight_l1, chroma_weight_l1, sizeof chroma_weight_l1); memcpy(h.chroma_offset_l1, chroma_offset_l1, sizeof chroma_offset_l1);
+    }
+};
+static std::map<CH264Picture *, std::vector<WHdr> > g_slice_hdrs;
 
 struct PicHdr {
     int32_t decode_idx, dst_surface, clear_surface, has_inter, deblock_enable, deblock_stop_mb;
@@ -91,6 +113,8 @@ static void put16(std::vector<int16_t> &v, const int32_t *src, int n, int shift_
 }
 static bool anynz(const int32_t *s, int n) { for (int i = 0; i < n; i++) if (s[i]) return true; return false; }
 
+static int g_cur_hdr_slice = -1;
+static WHdr g_saved_hdr;
 static void dump_picture(CH264PictureBase *pic, int deblock_enable, uint64_t sum_pre, uint64_t sum_post) {
     CH264SliceHeader &sh = pic->m_h264_slice_header;
     const int W = pic->PicWidthInMbs, nmb = pic->PicSizeInMbs;
@@ -216,7 +240,10 @@ static void dump_picture(CH264PictureBase *pic, int deblock_enable, uint64_t sum
                     ri[l] = (int8_t)s;
                 }
             }
-            // ---- prediction weights (IP:538-546, 2545-2610) ----
+            // ---- prediction weights (IP:538-546, 2545-2610), with the header of the slice this macroblock belongs to ----
+            std::vector<WHdr> &hdrs = g_slice_hdrs[pic->m_parent];
+            const bool swap_hdr = mb.slice_number >= 0 && (size_t)mb.slice_number < hdrs.size() && hdrs.size() > 1;
+            if (swap_hdr && g_cur_hdr_slice != mb.slice_number) { if (g_cur_hdr_slice == -1) g_saved_hdr.load(pic->m_h264_slice_header); hdrs[mb.slice_number].store(pic->m_h264_slice_header); g_cur_hdr_slice = mb.slice_number; }
             int st = sh.slice_type % 5;
             int logWD[3] = {0,0,0}, w0[3] = {1,1,1}, w1[3] = {1,1,1}, o0[3] = {0,0,0}, o1[3] = {0,0,0};
             bool derive = (sh.m_pps.weighted_pred_flag == 1 && (st == 0 || st == 3)) || (sh.m_pps.weighted_bipred_idc > 0 && st == 1);
@@ -268,6 +295,8 @@ static void dump_picture(CH264PictureBase *pic, int deblock_enable, uint64_t sum
         }
     }
     pic->CurrMbAddr = save_addr; pic->mb_x = save_mbx; pic->mb_y = save_mby;
+    if (g_cur_hdr_slice != -1) { g_saved_hdr.store(pic->m_h264_slice_header); g_cur_hdr_slice = -1; }
+    g_slice_hdrs.erase(pic->m_parent);
 
     // ---- scaling: LevelScale in list order (PB:4852-4989 restated per scan position) ----
     bool flat = true;
@@ -342,6 +371,7 @@ extern "C" int __wrap__ZN16CH264PictureBase25Deblocking_filter_processEv(CH264Pi
 extern "C" int __real__ZN12CH264Picture16decode_one_sliceER16CH264SliceHeaderR10CBitstreamRA16_PS_(CH264Picture *, CH264SliceHeader *, CBitstream *, CH264Picture **);
 extern "C" int __wrap__ZN12CH264Picture16decode_one_sliceER16CH264SliceHeaderR10CBitstreamRA16_PS_(CH264Picture *self, CH264SliceHeader *sh, CBitstream *bs, CH264Picture **dpb) {
     g_cur_pic = self;
+    if (g_replay) { WHdr w; w.load(*sh); g_slice_hdrs[self].push_back(w); }
     return __real__ZN12CH264Picture16decode_one_sliceER16CH264SliceHeaderR10CBitstreamRA16_PS_(self, sh, bs, dpb);
 }
 

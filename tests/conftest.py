@@ -36,8 +36,13 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 FULL_DIR = os.path.join(ROOT, "oracle", "_ref", "replay")
 
 
-def golden_files():
-    return sorted(os.path.join(GOLDEN_DIR, f) for f in os.listdir(GOLDEN_DIR) if f.endswith(".rp.xz"))
+def golden_files(kind="bundled"):
+    """kind: "bundled" = 1080p prefixes of the reference's own streams, "synth" = small random-syntax streams
+    (tests/h264_writer.py, decoded by the reference), "all"."""
+    fs = sorted(os.path.join(GOLDEN_DIR, f) for f in os.listdir(GOLDEN_DIR) if f.endswith(".rp.xz"))
+    if kind == "all":
+        return fs
+    return [f for f in fs if os.path.basename(f).startswith("synth_") == (kind == "synth")]
 
 
 def full_files():

@@ -1,0 +1,424 @@
+"""A small H.264 *syntax* writer (CAVLC, progressive, I/P slices) for test streams.  TEST INFRASTRUCTURE.
+
+It does not encode video: it draws random but well-formed syntax elements (macroblock types incl. P sub-partitions 8x4/4x8/4x4,
+P_8x8ref0, Intra16x16 with every prediction mode, Intra4x4/8x8 with predicted and explicit modes, I_PCM, multiple slices per
+picture with their own deblocking parameters, several reference pictures, explicit weighted prediction, 8x8 transform) and
+serialises them as an Annex-B byte stream.  The UNMODIFIED reference decoder (oracle/_ref/ref_harness) then decodes the stream and
+its interpretation — whatever it is — becomes the golden answer the native front end and the CUDA engine must reproduce
+(tools/make_golden.py writes the fixtures).  The bundled streams never reach most of these paths.
+
+VLC tables are read from the product's generated table file (h264_tables.inc, probed from the compiled reference)."""
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_tables():
+    txt = open(os.path.join(ROOT, "h264_video_decoder_demo_b200", "csrc", "host", "h264_tables.inc")).read()
+
+    def arr(name, shape):
+        m = re.search(name + r"[^=]*=\s*(\{.*?\});", txt, flags=re.S)
+        nums = [int(x) for x in re.findall(r"-?\d+", m.group(1))]
+        return np.array(nums).reshape(shape)
+
+    return {"coeff_token": arr("kCoeffToken", (6, 17, 4, 2)), "total_zeros": arr("kTotalZeros", (3, 16, 16, 2)),
+            "run_before": arr("kRunBefore", (8, 15, 2)), "me_cbp": arr("kMeCbp", (48, 2))}
+
+
+T = _load_tables()
+BLK_X = [0, 4, 0, 4, 8, 12, 8, 12, 0, 4, 0, 4, 8, 12, 8, 12]
+BLK_Y = [0, 0, 4, 4, 0, 0, 4, 4, 8, 8, 12, 12, 8, 8, 12, 12]
+
+
+class Bits:
+    def __init__(self):
+        self.b = []
+
+    def u(self, n, v):
+        for i in range(n - 1, -1, -1):
+            self.b.append((v >> i) & 1)
+
+    def ue(self, v):
+        v += 1
+        n = v.bit_length()
+        self.u(n - 1, 0)
+        self.u(n, v)
+
+    def se(self, v):
+        self.ue(2 * v - 1 if v > 0 else -2 * v)
+
+    def code(self, length, value):
+        self.u(int(length), int(value))
+
+    def trailing(self):
+        self.b.append(1)
+        while len(self.b) % 8:
+            self.b.append(0)
+
+    def align_zero(self):
+        while len(self.b) % 8:
+            self.b.append(0)
+
+    def rbsp(self):
+        assert len(self.b) % 8 == 0
+        return bytes(int("".join(map(str, self.b[i:i + 8])), 2) for i in range(0, len(self.b), 8))
+
+
+def nal(nal_ref_idc, nal_type, rbsp, long_start=True):
+    out = bytearray(b"\x00\x00\x00\x01" if long_start else b"\x00\x00\x01")
+    out.append((nal_ref_idc << 5) | nal_type)
+    zeros = 0
+    for byte in rbsp:
+        if zeros >= 2 and byte <= 3:
+            out.append(3)
+            zeros = 0
+        out.append(byte)
+        zeros = zeros + 1 if byte == 0 else 0
+    return bytes(out)
+
+
+class Stream:
+    """Random syntax for `n_pics` pictures of wmb x hmb macroblocks."""
+
+    def __init__(self, seed, wmb=8, hmb=6, n_pics=5, t8x8=False, weighted=False, n_refs=3, max_slices=3, pcm=True, poc_type=2):
+        self.rng = np.random.default_rng(seed)
+        self.wmb, self.hmb, self.n_pics = wmb, hmb, n_pics
+        self.t8x8, self.weighted, self.n_refs, self.max_slices, self.pcm, self.poc_type = t8x8, weighted, n_refs, max_slices, pcm, poc_type
+        self.out = bytearray()
+        self.trace = []            # (picture, mb address, kind) of every macroblock written, for debugging
+
+    # ---------------------------------------------------------------- parameter sets
+    def sps(self):
+        b = Bits()
+        b.u(8, 100); b.u(8, 0); b.u(8, 30); b.ue(0)                 # High profile (8x8 transform allowed), level 3
+        b.ue(1); b.ue(0); b.ue(0); b.u(1, 0); b.u(1, 0)             # 4:2:0, 8 bit, no bypass, no scaling matrix
+        b.ue(4)                                                      # log2_max_frame_num_minus4 -> 8 bits
+        b.ue(self.poc_type)
+        if self.poc_type == 0:
+            b.ue(4)
+        b.ue(self.n_refs); b.u(1, 0)
+        b.ue(self.wmb - 1); b.ue(self.hmb - 1)
+        b.u(1, 1); b.u(1, 1); b.u(1, 0)                              # frame_mbs_only, direct_8x8_inference, no cropping
+        b.u(1, 1)                                                    # VUI: only the bitstream restriction (max_num_reorder_frames = 0)
+        for _ in range(4):
+            b.u(1, 0)
+        b.u(1, 0); b.u(1, 0); b.u(1, 0); b.u(1, 0)                   # timing, nal hrd, vcl hrd, pic_struct
+        b.u(1, 1); b.u(1, 1); b.ue(0); b.ue(0); b.ue(10); b.ue(10); b.ue(0); b.ue(self.n_refs)
+        b.trailing()
+        return nal(3, 7, b.rbsp())
+
+    def pps(self):
+        b = Bits()
+        b.ue(0); b.ue(0); b.u(1, 0); b.u(1, 0); b.ue(0)              # CAVLC, no bottom-field poc, one slice group
+        b.ue(self.n_refs - 1); b.ue(0)
+        b.u(1, 1 if self.weighted else 0); b.u(2, 0)
+        b.se(0); b.se(0); b.se(int(self.rng.integers(-3, 4)))
+        b.u(1, 1); b.u(1, 0); b.u(1, 0)                              # deblocking control present, no constrained intra, no redundant pics
+        b.u(1, 1 if self.t8x8 else 0); b.u(1, 0); b.se(int(self.rng.integers(-3, 4)))
+        b.trailing()
+        return nal(3, 8, b.rbsp())
+
+    # ---------------------------------------------------------------- residual
+    def _nC(self, tc_map, avail, mbx, mby, bx, by, slice_of, cur_slice):
+        """tc_map: per-4x4 TotalCoeff array of the picture plane; bx,by: block coordinates in the plane."""
+        vals = []
+        for dx, dy in ((-1, 0), (0, -1)):
+            x, y = bx + dx, by + dy
+            if x < 0 or y < 0:
+                continue
+            per = tc_map.shape[1] // self.wmb
+            if slice_of[y // per, x // per] != cur_slice:
+                continue
+            vals.append(int(tc_map[y, x]))
+        if len(vals) == 2:
+            return (vals[0] + vals[1] + 1) >> 1
+        return vals[0] if vals else 0
+
+    def _levels(self, n, maxc):
+        """n non-zero levels placed in a list of maxc coefficients."""
+        lv = [0] * maxc
+        pos = sorted(self.rng.choice(maxc, size=n, replace=False).tolist())
+        for p in pos:
+            mag = 1 if self.rng.random() < 0.6 else int(self.rng.integers(1, 24))
+            lv[p] = mag if self.rng.random() < 0.5 else -mag
+        return lv
+
+    def _write_block(self, b, lv, nC, maxc):
+        nz = [(i, v) for i, v in enumerate(lv) if v]
+        tc = len(nz)
+        t1 = 0
+        for _, v in reversed(nz):
+            if abs(v) == 1 and t1 < 3:
+                t1 += 1
+            else:
+                break
+        cls = 4 if nC < 0 else 0 if nC < 2 else 1 if nC < 4 else 2 if nC < 8 else 3
+        ln, code = T["coeff_token"][cls][tc][t1]
+        assert ln > 0
+        b.code(ln, code)
+        if tc == 0:
+            return 0
+        levels = [v for _, v in reversed(nz)]                      # highest frequency first
+        for v in levels[:t1]:
+            b.u(1, 1 if v < 0 else 0)
+        sl = 1 if (tc > 10 and t1 < 3) else 0
+        for i, v in enumerate(levels[t1:]):
+            code_ = 2 * v - 2 if v > 0 else -2 * v - 1
+            if i == 0 and t1 < 3:
+                code_ -= 2
+            if sl == 0:
+                if code_ < 14:
+                    b.u(code_, 0); b.u(1, 1)
+                elif code_ < 30:
+                    b.u(14, 0); b.u(1, 1); b.u(4, code_ - 14)
+                else:
+                    b.u(15, 0); b.u(1, 1); b.u(12, code_ - 30)
+            else:
+                if (code_ >> sl) < 15:
+                    b.u(code_ >> sl, 0); b.u(1, 1); b.u(sl, code_ & ((1 << sl) - 1))
+                else:
+                    b.u(15, 0); b.u(1, 1); b.u(12, code_ - (15 << sl))
+            if sl == 0:
+                sl = 1
+            if abs(v) > (3 << (sl - 1)) and sl < 6:
+                sl += 1
+        last = nz[-1][0]
+        total_zeros = last + 1 - tc
+        if tc < maxc:
+            kind = 1 if maxc == 4 else 0
+            ln, code = T["total_zeros"][kind][tc][total_zeros]
+            assert ln > 0, (kind, tc, total_zeros)
+            b.code(ln, code)
+        zeros_left = total_zeros
+        idx = [i for i, _ in nz]
+        for k in range(tc - 1, 0, -1):
+            if zeros_left <= 0:
+                break
+            run = idx[k] - idx[k - 1] - 1
+            ln, code = T["run_before"][min(zeros_left, 7)][run]
+            assert ln > 0
+            b.code(ln, code)
+            zeros_left -= run
+        return tc
+
+    # ---------------------------------------------------------------- one picture
+    def picture(self, pic_idx, frame_num):
+        rng = self.rng
+        idr = pic_idx == 0
+        n_mbs = self.wmb * self.hmb
+        n_slices = int(rng.integers(1, self.max_slices + 1))
+        cuts = sorted(set([0] + rng.choice(np.arange(1, n_mbs), size=n_slices - 1, replace=False).tolist())) if n_slices > 1 else [0]
+        slice_of = np.zeros((self.hmb, self.wmb), dtype=np.int32)
+        for s, c in enumerate(cuts):
+            for a in range(c, cuts[s + 1] if s + 1 < len(cuts) else n_mbs):
+                slice_of[a // self.wmb, a % self.wmb] = s
+        tcY = np.zeros((self.hmb * 4, self.wmb * 4), dtype=np.int32)
+        tcC = [np.zeros((self.hmb * 2, self.wmb * 2), dtype=np.int32) for _ in range(2)]
+        n_avail_refs = min(pic_idx, self.n_refs)
+        # The reference builds the reference lists once per picture, from the FIRST slice's header (H264SliceData.cpp:84-124), and
+        # its CAVLC te() range for ref_idx comes from that list length (H264MacroBlock.cpp:1321): all slices of a picture share
+        # the slice type and num_ref_idx_active here, otherwise the reference itself loses synchronisation.
+        pic_is_p = (not idr) and rng.random() < 0.85
+        pic_n_act = int(rng.integers(1, n_avail_refs + 1)) if pic_is_p else 1
+        for s, first in enumerate(cuts):
+            last = (cuts[s + 1] if s + 1 < len(cuts) else n_mbs) - 1
+            is_p = pic_is_p
+            b = Bits()
+            b.ue(first); b.ue(0 if is_p else 2); b.ue(0)
+            b.u(8, frame_num)
+            if idr:
+                b.ue(0)
+            if self.poc_type == 0:
+                b.u(8, (2 * pic_idx) & 255)
+            n_act = 1
+            if is_p:
+                n_act = pic_n_act
+                b.u(1, 1); b.ue(n_act - 1)                          # num_ref_idx_active_override
+                b.u(1, 0)                                            # no list modification
+                if self.weighted:
+                    ld, cd = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+                    b.ue(ld); b.ue(cd)
+                    for _ in range(n_act):
+                        if rng.random() < 0.6:
+                            b.u(1, 1); b.se(int(rng.integers(-20, 60))); b.se(int(rng.integers(-10, 11)))
+                        else:
+                            b.u(1, 0)
+                        if rng.random() < 0.5:
+                            b.u(1, 1)
+                            for _ in range(2):
+                                b.se(int(rng.integers(-20, 60))); b.se(int(rng.integers(-10, 11)))
+                        else:
+                            b.u(1, 0)
+            if idr:
+                b.u(1, 0); b.u(1, 0)
+            else:
+                b.u(1, 0)                                            # sliding window
+            qp = 26 + int(rng.integers(-8, 9))
+            b.se(qp - 26)
+            idc = int(rng.integers(0, 3))
+            b.ue(idc)
+            if idc != 1:
+                b.se(int(rng.integers(-3, 4))); b.se(int(rng.integers(-3, 4)))
+            # ---- slice data
+            skip_run = 0
+            for a in range(first, last + 1):
+                mbx, mby = a % self.wmb, a // self.wmb
+                left_ok = mbx > 0 and slice_of[mby, mbx - 1] == s
+                top_ok = mby > 0 and slice_of[mby - 1, mbx] == s
+                if is_p and rng.random() < 0.25:
+                    skip_run += 1
+                    self.trace.append((pic_idx, a, "skip"))
+                    continue
+                if is_p:
+                    b.ue(skip_run); skip_run = 0
+                kind = rng.random()
+                self.trace.append((pic_idx, a, "inter" if (is_p and kind < 0.7) else "intra"))
+                if is_p and kind < 0.7:
+                    qp = self._inter_mb(b, n_act, qp, tcY, tcC, mbx, mby, slice_of, s)
+                else:
+                    qp = self._intra_mb(b, is_p, qp, tcY, tcC, mbx, mby, slice_of, s, left_ok, top_ok)
+            if is_p and skip_run:
+                b.ue(skip_run)
+            b.trailing()
+            self.out += nal(1, 5 if idr else 1, b.rbsp(), long_start=(s == 0))
+
+    def _residual(self, b, cbp_luma, cbp_chroma, i16, t8, qp, tcY, tcC, mbx, mby, slice_of, s):
+        rng = self.rng
+        if i16:
+            n = int(rng.integers(0, 7))
+            nC = self._nC(tcY, None, mbx, mby, mbx * 4, mby * 4, slice_of, s)
+            self._write_block(b, self._levels(n, 16), nC, 16)
+        for i8 in range(4):
+            if not (cbp_luma >> i8) & 1:
+                continue
+            for i4 in range(4):
+                blk = i8 * 4 + i4
+                bx, by = mbx * 4 + BLK_X[blk] // 4, mby * 4 + BLK_Y[blk] // 4
+                nC = self._nC(tcY, None, mbx, mby, bx, by, slice_of, s)
+                maxc = 15 if i16 else 16
+                n = int(rng.integers(0, 5)) if rng.random() < 0.8 else int(rng.integers(5, maxc + 1))
+                tcY[by, bx] = self._write_block(b, self._levels(n, maxc), nC, maxc)
+        if cbp_chroma:
+            for c in range(2):
+                self._write_block(b, self._levels(int(rng.integers(0, 4)), 4), -1, 4)
+        if cbp_chroma == 2:
+            for c in range(2):
+                for blk in range(4):
+                    bx, by = mbx * 2 + blk % 2, mby * 2 + blk // 2
+                    nC = self._nC(tcC[c], None, mbx, mby, bx, by, slice_of, s)
+                    n = int(rng.integers(0, 4))
+                    tcC[c][by, bx] = self._write_block(b, self._levels(n, 15), nC, 15)
+
+    def _cbp_and_residual(self, b, intra_nxn, t8_allowed, qp, tcY, tcC, mbx, mby, slice_of, s, t8_known=None):
+        rng = self.rng
+        cbp_luma = int(rng.integers(0, 16)) if rng.random() < 0.8 else 0
+        cbp_chroma = int(rng.integers(0, 3))
+        cbp = cbp_luma | (cbp_chroma << 4)
+        col = 0 if intra_nxn else 1
+        code_num = int(np.nonzero(T["me_cbp"][:, col] == cbp)[0][0])
+        b.ue(code_num)
+        t8 = t8_known
+        if t8_known is None and cbp_luma > 0 and self.t8x8 and t8_allowed:
+            t8 = int(rng.random() < 0.5)
+            b.u(1, t8)
+        if cbp:
+            dq = int(rng.integers(-2, 3)) if rng.random() < 0.3 else 0
+            if not 12 <= qp + dq <= 44:
+                dq = 0
+            b.se(dq)
+            qp += dq
+            self._residual(b, cbp_luma, cbp_chroma, False, t8, qp, tcY, tcC, mbx, mby, slice_of, s)
+        return qp
+
+    def _inter_mb(self, b, n_act, qp, tcY, tcC, mbx, mby, slice_of, s):
+        rng = self.rng
+        t = int(rng.choice([0, 1, 2, 3, 3, 3, 4]))
+        b.ue(t)
+        no_sub8 = True
+
+        def mvd():
+            for _ in range(2):
+                b.se(int(rng.integers(-5, 6)) if rng.random() < 0.7 else 0)
+
+        def ref():
+            if n_act > 1:
+                r = int(rng.integers(0, n_act))
+                if n_act == 2:
+                    b.u(1, 0 if r else 1)
+                else:
+                    b.ue(r)
+        if t <= 2:
+            parts = 1 if t == 0 else 2
+            for _ in range(parts):
+                ref()
+            for _ in range(parts):
+                mvd()
+        else:
+            subs = [int(rng.integers(0, 4)) for _ in range(4)]
+            for st in subs:
+                b.ue(st)
+                if st:
+                    no_sub8 = False
+            if t == 3:
+                for _ in range(4):
+                    ref()
+            for st in subs:
+                for _ in range((1, 2, 2, 4)[st]):
+                    mvd()
+        return self._cbp_and_residual(b, False, no_sub8, qp, tcY, tcC, mbx, mby, slice_of, s)
+
+    def _intra_mb(self, b, is_p, qp, tcY, tcC, mbx, mby, slice_of, s, left_ok, top_ok):
+        rng = self.rng
+        off = 5 if is_p else 0
+        kind = rng.random()
+        if self.pcm and kind < 0.08:
+            b.ue(off + 25)
+            b.align_zero()
+            for _ in range(384):
+                b.u(8, int(rng.integers(0, 256)))
+            tcY[mby * 4:mby * 4 + 4, mbx * 4:mbx * 4 + 4] = 0
+            return qp
+        diag_ok = left_ok and top_ok and slice_of[mby - 1, mbx - 1] == s
+        chroma_mode = int(rng.integers(0, 4 if diag_ok else 3)) if (left_ok and top_ok) else 0
+        if kind < 0.5:
+            modes = [2]
+            if top_ok:
+                modes.append(0)
+            if left_ok:
+                modes.append(1)
+            if diag_ok:
+                modes.append(3)
+            pm = int(rng.choice(modes))
+            cbp_chroma = int(rng.integers(0, 3))
+            cbp_luma = 15 if rng.random() < 0.5 else 0
+            b.ue(off + 1 + pm + 4 * cbp_chroma + (12 if cbp_luma else 0))
+            b.ue(chroma_mode)
+            dq = int(rng.integers(-2, 3)) if rng.random() < 0.3 else 0
+            if not 12 <= qp + dq <= 44:
+                dq = 0
+            b.se(dq)
+            qp += dq
+            self._residual(b, cbp_luma, cbp_chroma, True, 0, qp, tcY, tcC, mbx, mby, slice_of, s)
+            return qp
+        b.ue(off + 0)
+        t8 = 0
+        if self.t8x8:
+            t8 = int(rng.random() < 0.5)
+            b.u(1, t8)
+        for blk in range(4 if t8 else 16):
+            inner = (blk == 3) if t8 else (BLK_X[blk] > 0 and BLK_Y[blk] > 0)
+            if inner and rng.random() < 0.6:
+                b.u(1, 0); b.u(3, int(rng.integers(0, 8)))
+            else:
+                b.u(1, 1)
+        b.ue(chroma_mode)
+        return self._cbp_and_residual(b, True, False, qp, tcY, tcC, mbx, mby, slice_of, s, t8_known=t8)
+
+    def build(self):
+        self.out += self.sps() + self.pps()
+        for p in range(self.n_pics):
+            self.picture(p, p & 255)
+        return bytes(self.out)

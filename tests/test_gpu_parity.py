@@ -32,7 +32,7 @@ def _run_stream(eng, rs, sid=0, check_pre=False):
     return bad
 
 
-@pytest.mark.parametrize("path", golden_files(), ids=os.path.basename)
+@pytest.mark.parametrize("path", golden_files("all"), ids=os.path.basename)
 def test_golden_fixture_bit_exact(path):
     rp = replay.load_replay(path)
     eng = engine.Engine(0, 1, rp.width_mbs, rp.height_mbs)

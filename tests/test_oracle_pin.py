@@ -33,7 +33,7 @@ def _check(path):
     return os.path.basename(path), len(rp.pictures), bad, out_bad
 
 
-@pytest.mark.parametrize("path", golden_files(), ids=os.path.basename)
+@pytest.mark.parametrize("path", golden_files("all"), ids=os.path.basename)
 def test_oracle_matches_reference_on_golden_fixture(path):
     name, n, bad, out_bad = _check(path)
     assert n > 0 and not bad and not out_bad, f"{name}: pictures {bad} / output frames {out_bad} differ from the reference"
