@@ -101,6 +101,7 @@ struct SliceHeader {
     int ref_pic_list_modification_flag[2] = {0, 0}, modification_count[2] = {0, 0};
     int modification_of_pic_nums_idc[2][33], abs_diff_pic_num_minus1[2][33], long_term_pic_num[2][33];
     int luma_log2_weight_denom = 0, chroma_log2_weight_denom = 0;
+    int last_luma_weight_flag[2] = {0, 0};      // luma_weight_lX_flag of the last entry parsed: what luma_weight_lX[-1] reads in the reference (Q8)
     int luma_weight[2][32], luma_offset[2][32], chroma_weight[2][32][2], chroma_offset[2][32][2];
     int no_output_of_prior_pics_flag = 0, long_term_reference_flag = 0, adaptive_ref_pic_marking_mode_flag = 0, mmco_count = 0;
     Mmco mmco[33];

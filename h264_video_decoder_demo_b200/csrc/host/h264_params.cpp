@@ -230,7 +230,8 @@ int parse_slice_header(BitReader &br, int nal_ref_idc, int nal_unit_type, const 
             const int n = l ? sh.num_ref_idx_l1_active_minus1 : sh.num_ref_idx_l0_active_minus1;
             for (int i = 0; i <= n; i++) {
                 sh.luma_weight[l][i] = 1 << sh.luma_log2_weight_denom; sh.luma_offset[l][i] = 0;
-                if (br.u1()) { sh.luma_weight[l][i] = br.se(); sh.luma_offset[l][i] = br.se(); }
+                sh.last_luma_weight_flag[l] = br.u1();
+                if (sh.last_luma_weight_flag[l]) { sh.luma_weight[l][i] = br.se(); sh.luma_offset[l][i] = br.se(); }
                 if (sps.ChromaArrayType != 0) {
                     sh.chroma_weight[l][i][0] = sh.chroma_weight[l][i][1] = 1 << sh.chroma_log2_weight_denom; sh.chroma_offset[l][i][0] = sh.chroma_offset[l][i][1] = 0;
                     if (br.u1()) for (int j = 0; j < 2; j++) { sh.chroma_weight[l][i][j] = br.se(); sh.chroma_offset[l][i][j] = br.se(); }

@@ -871,8 +871,11 @@ struct Dec {
             } else if (explicitMode) {
                 const bool half = mbaff && mbs[cur].field;
                 const int r0 = half ? ref0 >> 1 : ref0, r1 = half ? ref1 >> 1 : ref1;
-                auto lw = [&](int l, int r) { return (r >= 0 && r < 32) ? sh.luma_weight[l][r] : 0; };
-                auto lo = [&](int l, int r) { return (r >= 0 && r < 32) ? sh.luma_offset[l][r] : 0; };
+                // REF Q8: a list-1-only partition takes its LUMA weight/offset from luma_weight_l0[refIdxL0] / luma_offset_l0[refIdxL0] with
+                // refIdxL0 == -1 (IP:2764/2768 + IP:3003-3006), i.e. the struct members in front of the arrays (H264SliceHeader.h:78-80):
+                // luma_weight_l0[-1] is luma_weight_l0_flag as last parsed, luma_offset_l0[-1] is luma_weight_l0[31]
+                auto lw = [&](int l, int r) { return (r >= 0 && r < 32) ? sh.luma_weight[l][r] : (r == -1 ? sh.last_luma_weight_flag[l] : 0); };
+                auto lo = [&](int l, int r) { return (r >= 0 && r < 32) ? sh.luma_offset[l][r] : (r == -1 ? sh.luma_weight[l][31] : 0); };
                 auto cw = [&](int l, int r, int j) { return (r >= 0 && r < 32) ? sh.chroma_weight[l][r][j] : 0; };
                 auto co = [&](int l, int r, int j) { return (r >= 0 && r < 32) ? sh.chroma_offset[l][r][j] : 0; };
                 logWD[0] = sh.luma_log2_weight_denom; w0[0] = lw(0, r0); w1[0] = lw(1, r1); o0[0] = lo(0, r0); o1[0] = lo(1, r1);

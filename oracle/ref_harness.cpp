@@ -64,11 +64,12 @@ static long g_dump_pix_idx = -1;
 // every slice's header, in the order slice_data() numbered them: the picture object only keeps the LAST slice's header, but
 // weights / slice type are per slice (multi-slice pictures with explicit weighted prediction)
 struct WHdr {   // the per-slice fields the weight derivation reads (plain copies: CH264SliceHeader owns malloc'ed maps)
-    int32_t slice_type, luma_log2_weight_denom, chroma_log2_weight_denom;
+    int32_t slice_type, luma_log2_weight_denom, chroma_log2_weight_denom, luma_weight_l0_flag, luma_weight_l1_flag;
     int32_t luma_weight_l0[32], luma_offset_l0[32], chroma_weight_l0[32][2], chroma_offset_l0[32][2];
     int32_t luma_weight_l1[32], luma_offset_l1[32], chroma_weight_l1[32][2], chroma_offset_l1[32][2];
     void load(const CH264SliceHeader &h) {
         slice_type = h.slice_type; luma_log2_weight_denom = h.luma_log2_weight_denom; chroma_log2_weight_denom = h.chroma_log2_weight_denom;
+        luma_weight_l0_flag = h.luma_weight_l0_flag; luma_weight_l1_flag = h.luma_weight_l1_flag;      // read as luma_weight_lX[-1] (Q8)
         memcpy(luma_weight_l0, h.luma_weight_l0, sizeof luma_weight_l0); memcpy(luma_offset_l0, h.luma_offset_l0, sizeof luma_offset_l0);
         memcpy(chroma_weight_l0, h.chroma_weight_l0, sizeof chroma_weight_l0); memcpy(chroma_offset_l0, h.chroma_offset_l0, sizeof chroma_offset_l0);
         memcpy(luma_weight_l1, h.luma_weight_l1, sizeof luma_weight_l1); memcpy(luma_offset_l1, h.luma_offset_l1, sizeof luma_offset_l1);
@@ -76,6 +77,7 @@ struct WHdr {   // the per-slice fields the weight derivation reads (plain copie
     }
     void store(CH264SliceHeader &h) const {
         h.slice_type = slice_type; h.luma_log2_weight_denom = luma_log2_weight_denom; h.chroma_log2_weight_denom = chroma_log2_weight_denom;
+        h.luma_weight_l0_flag = luma_weight_l0_flag; h.luma_weight_l1_flag = luma_weight_l1_flag;
         memcpy(h.luma_weight_l0, luma_weight_l0, sizeof luma_weight_l0); memcpy(h.luma_offset_l0, luma_offset_l0, sizeof luma_offset_l0);
         memcpy(h.chroma_weight_l0, chroma_weight_l0, sizeof chroma_weight_l0); memcpy(h.chroma_offset_l0, chroma_offset_l0, sizeof chroma_offset_l0);
         memcpy(h.luma_weight_l1, luma_weight_l1, sizeof luma_weight_l1); memcpy(h.luma_offset_l1, luma_offset_l1, sizeof luma_offset_l1);

@@ -83,10 +83,13 @@ def nal(nal_ref_idc, nal_type, rbsp, long_start=True):
 class Stream:
     """Random syntax for `n_pics` pictures of wmb x hmb macroblocks."""
 
-    def __init__(self, seed, wmb=8, hmb=6, n_pics=5, t8x8=False, weighted=False, n_refs=3, max_slices=3, pcm=True, poc_type=2):
+    def __init__(self, seed, wmb=8, hmb=6, n_pics=5, t8x8=False, weighted=False, n_refs=3, max_slices=3, pcm=True, poc_type=2, bframes=False, bipred_idc=0):
         self.rng = np.random.default_rng(seed)
         self.wmb, self.hmb, self.n_pics = wmb, hmb, n_pics
         self.t8x8, self.weighted, self.n_refs, self.max_slices, self.pcm, self.poc_type = t8x8, weighted, n_refs, max_slices, pcm, poc_type
+        self.bframes, self.bipred_idc = bframes, bipred_idc
+        if bframes:
+            self.poc_type = 0
         self.out = bytearray()
         self.trace = []            # (picture, mb address, kind) of every macroblock written, for debugging
 
@@ -106,7 +109,7 @@ class Stream:
         for _ in range(4):
             b.u(1, 0)
         b.u(1, 0); b.u(1, 0); b.u(1, 0); b.u(1, 0)                   # timing, nal hrd, vcl hrd, pic_struct
-        b.u(1, 1); b.u(1, 1); b.ue(0); b.ue(0); b.ue(10); b.ue(10); b.ue(0); b.ue(self.n_refs)
+        b.u(1, 1); b.u(1, 1); b.ue(0); b.ue(0); b.ue(10); b.ue(10); b.ue(2 if self.bframes else 0); b.ue(self.n_refs)
         b.trailing()
         return nal(3, 7, b.rbsp())
 
@@ -114,7 +117,7 @@ class Stream:
         b = Bits()
         b.ue(0); b.ue(0); b.u(1, 0); b.u(1, 0); b.ue(0)              # CAVLC, no bottom-field poc, one slice group
         b.ue(self.n_refs - 1); b.ue(0)
-        b.u(1, 1 if self.weighted else 0); b.u(2, 0)
+        b.u(1, 1 if self.weighted else 0); b.u(2, self.bipred_idc)
         b.se(0); b.se(0); b.se(int(self.rng.integers(-3, 4)))
         b.u(1, 1); b.u(1, 0); b.u(1, 0)                              # deblocking control present, no constrained intra, no redundant pics
         b.u(1, 1 if self.t8x8 else 0); b.u(1, 0); b.se(int(self.rng.integers(-3, 4)))
@@ -205,9 +208,13 @@ class Stream:
         return tc
 
     # ---------------------------------------------------------------- one picture
-    def picture(self, pic_idx, frame_num):
+    def picture(self, pic_idx, frame_num, kind="P", poc=None, is_ref=True, refs_before=0, refs_after=0):
+        """kind: "I" (IDR when pic_idx == 0), "P" or "B"; refs_before / refs_after: reference pictures available with a smaller /
+        larger POC (B pictures)."""
         rng = self.rng
         idr = pic_idx == 0
+        is_b = kind == "B"
+        poc = 2 * pic_idx if poc is None else poc
         n_mbs = self.wmb * self.hmb
         n_slices = int(rng.integers(1, self.max_slices + 1))
         cuts = sorted(set([0] + rng.choice(np.arange(1, n_mbs), size=n_slices - 1, replace=False).tolist())) if n_slices > 1 else [0]
@@ -217,24 +224,48 @@ class Stream:
                 slice_of[a // self.wmb, a % self.wmb] = s
         tcY = np.zeros((self.hmb * 4, self.wmb * 4), dtype=np.int32)
         tcC = [np.zeros((self.hmb * 2, self.wmb * 2), dtype=np.int32) for _ in range(2)]
-        n_avail_refs = min(pic_idx, self.n_refs)
+        n_avail_refs = min(refs_before + refs_after, self.n_refs) if self.bframes else min(pic_idx, self.n_refs)
+        if is_b and self.bipred_idc == 2:
+            n_avail_refs = 1         # implicit weights: the reference divides by the POC distance of the two references before testing it
+                                     # for 0 (IP:2957), so both lists keep one entry: the nearest picture before / after
         # The reference builds the reference lists once per picture, from the FIRST slice's header (H264SliceData.cpp:84-124), and
         # its CAVLC te() range for ref_idx comes from that list length (H264MacroBlock.cpp:1321): all slices of a picture share
         # the slice type and num_ref_idx_active here, otherwise the reference itself loses synchronisation.
-        pic_is_p = (not idr) and rng.random() < 0.85
+        pic_is_p = (not idr) and (is_b or kind == "P") and (self.bframes or rng.random() < 0.85)
         pic_n_act = int(rng.integers(1, n_avail_refs + 1)) if pic_is_p else 1
+        pic_n_act1 = int(rng.integers(1, n_avail_refs + 1)) if is_b else 1
         for s, first in enumerate(cuts):
             last = (cuts[s + 1] if s + 1 < len(cuts) else n_mbs) - 1
             is_p = pic_is_p
             b = Bits()
-            b.ue(first); b.ue(0 if is_p else 2); b.ue(0)
+            b.ue(first); b.ue((1 if is_b else 0) if is_p else 2); b.ue(0)
             b.u(8, frame_num)
             if idr:
                 b.ue(0)
             if self.poc_type == 0:
-                b.u(8, (2 * pic_idx) & 255)
-            n_act = 1
-            if is_p:
+                b.u(8, poc & 255)
+            n_act = n_act1 = 1
+            if is_p and is_b:
+                n_act, n_act1 = pic_n_act, pic_n_act1
+                b.u(1, 1)                                            # direct_spatial_mv_pred_flag
+                b.u(1, 1); b.ue(n_act - 1); b.ue(n_act1 - 1)
+                b.u(1, 0); b.u(1, 0)                                 # no modification of either list
+                if self.bipred_idc == 1:
+                    ld, cd = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+                    b.ue(ld); b.ue(cd)
+                    for cnt in (n_act, n_act1):
+                        for _ in range(cnt):
+                            if rng.random() < 0.6:
+                                b.u(1, 1); b.se(int(rng.integers(-20, 60))); b.se(int(rng.integers(-10, 11)))
+                            else:
+                                b.u(1, 0)
+                            if rng.random() < 0.5:
+                                b.u(1, 1)
+                                for _ in range(2):
+                                    b.se(int(rng.integers(-20, 60))); b.se(int(rng.integers(-10, 11)))
+                            else:
+                                b.u(1, 0)
+            elif is_p:
                 n_act = pic_n_act
                 b.u(1, 1); b.ue(n_act - 1)                          # num_ref_idx_active_override
                 b.u(1, 0)                                            # no list modification
@@ -254,7 +285,7 @@ class Stream:
                             b.u(1, 0)
             if idr:
                 b.u(1, 0); b.u(1, 0)
-            else:
+            elif is_ref:
                 b.u(1, 0)                                            # sliding window
             qp = 26 + int(rng.integers(-8, 9))
             b.se(qp - 26)
@@ -276,14 +307,17 @@ class Stream:
                     b.ue(skip_run); skip_run = 0
                 kind = rng.random()
                 self.trace.append((pic_idx, a, "inter" if (is_p and kind < 0.7) else "intra"))
-                if is_p and kind < 0.7:
+                kind = float(kind)
+                if is_p and is_b and kind < 0.75:
+                    qp = self._b_mb(b, n_act, n_act1, qp, tcY, tcC, mbx, mby, slice_of, s)
+                elif is_p and kind < 0.7:
                     qp = self._inter_mb(b, n_act, qp, tcY, tcC, mbx, mby, slice_of, s)
                 else:
-                    qp = self._intra_mb(b, is_p, qp, tcY, tcC, mbx, mby, slice_of, s, left_ok, top_ok)
+                    qp = self._intra_mb(b, is_p, qp, tcY, tcC, mbx, mby, slice_of, s, left_ok, top_ok, is_b)
             if is_p and skip_run:
                 b.ue(skip_run)
             b.trailing()
-            self.out += nal(1, 5 if idr else 1, b.rbsp(), long_start=(s == 0))
+            self.out += nal(1 if is_ref else 0, 5 if idr else 1, b.rbsp(), long_start=(s == 0))
 
     def _residual(self, b, cbp_luma, cbp_chroma, i16, t8, qp, tcY, tcC, mbx, mby, slice_of, s):
         rng = self.rng
@@ -370,9 +404,54 @@ class Stream:
                     mvd()
         return self._cbp_and_residual(b, False, no_sub8, qp, tcY, tcC, mbx, mby, slice_of, s)
 
-    def _intra_mb(self, b, is_p, qp, tcY, tcC, mbx, mby, slice_of, s, left_ok, top_ok):
+    def _b_mb(self, b, n0, n1, qp, tcY, tcC, mbx, mby, slice_of, s):
+        """A B macroblock: B_Direct_16x16, 16x16 / 16x8 / 8x16 with every list combination, B_8x8 with direct / L0 / L1 / Bi 8x8
+        sub-macroblocks (the reference rejects the smaller B sub-partitions, H264MacroBlock.cpp:1061)."""
         rng = self.rng
-        off = 5 if is_p else 0
+        L0, L1, BI = 1, 2, 3
+        pairs = [(L0, L0), (L1, L1), (L0, L1), (L1, L0), (L0, BI), (L1, BI), (BI, L0), (BI, L1), (BI, BI)]
+        t = int(rng.choice([0, 1, 2, 3] + list(range(4, 22)) + [22, 22, 22]))
+        b.ue(t)
+
+        def ref(n):
+            if n > 1:
+                r = int(rng.integers(0, n))
+                if n == 2:
+                    b.u(1, 0 if r else 1)
+                else:
+                    b.ue(r)
+
+        def mvd():
+            for _ in range(2):
+                b.se(int(rng.integers(-5, 6)) if rng.random() < 0.7 else 0)
+        if t == 0:
+            parts = []
+        elif t <= 3:
+            parts = [t]
+        elif t < 22:
+            parts = list(pairs[(t - 4) // 2])
+        else:
+            subs = [int(rng.integers(0, 4)) for _ in range(4)]
+            for st in subs:
+                b.ue(st)
+            parts = [st for st in subs if st]                        # sub type 1/2/3 = L0/L1/Bi 8x8; 0 = direct (nothing coded)
+        for p in parts:
+            if p & L0:
+                ref(n0)
+        for p in parts:
+            if p & L1:
+                ref(n1)
+        for p in parts:
+            if p & L0:
+                mvd()
+        for p in parts:
+            if p & L1:
+                mvd()
+        return self._cbp_and_residual(b, False, True, qp, tcY, tcC, mbx, mby, slice_of, s)
+
+    def _intra_mb(self, b, is_p, qp, tcY, tcC, mbx, mby, slice_of, s, left_ok, top_ok, is_b=False):
+        rng = self.rng
+        off = (23 if is_b else 5) if is_p else 0
         kind = rng.random()
         if self.pcm and kind < 0.08:
             b.ue(off + 25)
@@ -419,6 +498,26 @@ class Stream:
 
     def build(self):
         self.out += self.sps() + self.pps()
-        for p in range(self.n_pics):
-            self.picture(p, p & 255)
+        if not self.bframes:
+            for p in range(self.n_pics):
+                self.picture(p, p & 255)
+            return bytes(self.out)
+        # decode order I0 P4 B2 P8 B6 ... (POC = 2 x display index); every second B picture is itself a reference (B pyramid)
+        n_ref_done, ref_pocs, k, display = 0, [], 0, 0
+        plan = [("I", 0, True)]
+        d = 2
+        while len(plan) < self.n_pics:
+            plan.append(("P", 2 * d, True))
+            if len(plan) < self.n_pics:
+                plan.append(("B", 2 * d - 2, bool(self.rng.integers(0, 2))))
+            d += 2
+        for i, (kind, poc, is_ref) in enumerate(plan):
+            window = ref_pocs[-self.n_refs:]
+            before, after = sum(1 for q in window if q < poc), sum(1 for q in window if q > poc)
+            if kind == "B" and (before + after < 2 or (self.bipred_idc == 2 and (before < 1 or after < 1))):
+                kind = "P"
+            self.picture(i, n_ref_done & 255, kind=kind, poc=poc, is_ref=is_ref, refs_before=before, refs_after=after)
+            if is_ref:
+                n_ref_done += 1
+                ref_pocs.append(poc)
         return bytes(self.out)

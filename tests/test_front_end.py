@@ -128,7 +128,8 @@ def test_random_syntax_streams_against_the_live_reference(tmp_path):
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     if not os.path.exists(harness):
         pytest.skip("reference harness not built")
-    cfgs = [dict(), dict(t8x8=True, weighted=True, n_refs=4, poc_type=0, n_pics=5), dict(wmb=9, hmb=7, max_slices=4, n_pics=4), dict(weighted=True, wmb=5, hmb=4, n_pics=6, n_refs=4)]
+    cfgs = [dict(), dict(t8x8=True, weighted=True, n_refs=4, poc_type=0, n_pics=5), dict(wmb=9, hmb=7, max_slices=4, n_pics=4), dict(weighted=True, wmb=5, hmb=4, n_pics=6, n_refs=4),
+            dict(bframes=True, n_pics=7), dict(bframes=True, bipred_idc=2, n_pics=7, n_refs=4), dict(bframes=True, bipred_idc=1, weighted=True, n_pics=7, t8x8=True)]
     seed0 = int.from_bytes(os.urandom(3), "little")
     for k, cfg in enumerate(cfgs * 2):
         seed = seed0 + k

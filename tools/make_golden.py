@@ -44,14 +44,19 @@ def make_bitstream_prefixes(out_dir):
 SYNTH = [("synth_cavlc_ip", dict(seed=11, n_pics=5)),
          ("synth_t8x8_wp_poc0", dict(seed=12, t8x8=True, weighted=True, n_refs=4, poc_type=0, n_pics=6)),
          ("synth_slices_11x9", dict(seed=13, wmb=11, hmb=9, max_slices=5, n_pics=4)),
-         ("synth_wp_5x4", dict(seed=14, weighted=True, wmb=5, hmb=4, n_pics=8, n_refs=4))]
+         ("synth_wp_5x4", dict(seed=14, weighted=True, wmb=5, hmb=4, n_pics=8, n_refs=4)),
+         ("synth_b_direct", dict(seed=15, bframes=True, n_pics=7)),
+         ("synth_b_implicit", dict(seed=16, bframes=True, bipred_idc=2, n_pics=7, n_refs=4)),
+         ("synth_b_explicit_t8x8", dict(seed=17, bframes=True, bipred_idc=1, weighted=True, n_pics=7, t8x8=True)),
+         ("synth_b_explicit_6x5", dict(seed=18, bframes=True, bipred_idc=1, wmb=6, hmb=5, n_pics=9, max_slices=1))]
 
 
 def make_synthetic(out_dir):
     """Random-syntax CAVLC streams (tests/h264_writer.py) decoded by the UNMODIFIED reference (oracle/_ref/ref_harness): the stream and
     the reference's structure-of-arrays + picture checksums become fixtures.  They reach what the bundled streams never do: I_PCM,
     P sub-partitions 8x4/4x8/4x4, P_8x8ref0, every Intra16x16 mode, several slices per picture with idc 0/1/2 and offsets,
-    per-slice explicit weights, CAVLC with the 8x8 transform."""
+    per-slice explicit weights, CAVLC with the 8x8 transform; B pictures (reordered output, B pyramid) with every 16x16/16x8/8x16 list
+    combination, B_8x8 incl. direct sub-macroblocks, spatial direct, implicit and EXPLICIT bi-prediction weights (Q8 live)."""
     import lzma
     import subprocess
     import tempfile
