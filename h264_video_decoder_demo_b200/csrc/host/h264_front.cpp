@@ -445,7 +445,10 @@ void Front::emit_picture(int deblock_enable) {
     while (coefs.size() % 4) coefs.push_back(0);
     const size_t b_info = (size_t)nmb * sizeof(H264B2MbInfo), b_modes = (size_t)nmb * 8, b_coff = (size_t)nmb * 4, b_mot = has_inter ? (size_t)nmb * sizeof(H264B2MbMotion) : 0;
     const size_t b_w = weights.size() * sizeof(H264B2Weight), b_c = coefs.size() * 2, b_ls = flat ? 0 : (size_t)(2 * 2 * 6 * 16 + 2 * 2 * 6 * 64) * 2;
-    const size_t total = b_info + b_modes + b_coff + b_mot + b_w + b_c + b_ls;
+    // every array starts on a 64-byte boundary inside the block: the engine keeps host alignment on the device and its kernels
+    // read records with 16-byte loads
+    auto al = [](size_t n) { return (n + 63) & ~(size_t)63; };
+    const size_t total = al(b_info) + al(b_modes) + al(b_coff) + al(b_mot) + al(b_w) + al(b_c) + al(b_ls);
     size_t cap = 0;
     uint8_t *blk = get_block(total, &cap);
     H264B2FrontEvent e; memset(&e, 0, sizeof e);
@@ -461,13 +464,13 @@ void Front::emit_picture(int deblock_enable) {
     p.n_weights = ph.n_weights; p.n_coefs = ph.n_coefs; p.custom_scaling = ph.custom_scaling;
     if (blk) {
         uint8_t *q = blk;
-        memcpy(q, info.data(), b_info); p.mb_info = (const H264B2MbInfo *)q; q += b_info;
-        memcpy(q, modes.data(), b_modes); p.intra_modes = (const uint64_t *)q; q += b_modes;
-        memcpy(q, coff.data(), b_coff); p.coef_offset = (const uint32_t *)q; q += b_coff;
-        if (has_inter) { memcpy(q, s.motion.data(), b_mot); p.motion = (const H264B2MbMotion *)q; q += b_mot; }
-        memcpy(q, weights.data(), b_w); p.weights = (const H264B2Weight *)q; q += b_w;
+        memcpy(q, info.data(), b_info); p.mb_info = (const H264B2MbInfo *)q; q += al(b_info);
+        memcpy(q, modes.data(), b_modes); p.intra_modes = (const uint64_t *)q; q += al(b_modes);
+        memcpy(q, coff.data(), b_coff); p.coef_offset = (const uint32_t *)q; q += al(b_coff);
+        if (has_inter) { memcpy(q, s.motion.data(), b_mot); p.motion = (const H264B2MbMotion *)q; q += al(b_mot); }
+        memcpy(q, weights.data(), b_w); p.weights = (const H264B2Weight *)q; q += al(b_w);
         if (b_c) memcpy(q, coefs.data(), b_c);
-        p.coefs = (const int16_t *)q; q += b_c;
+        p.coefs = (const int16_t *)q; q += al(b_c);
         if (!flat) {
             // LevelScale in LIST order (PB:4852-4989 per scan position; chroma uses the luma list, Q7): [intra/inter][frame/field scan][qP%6][k]
             int16_t *ls4 = (int16_t *)q, *ls8 = ls4 + 2 * 2 * 6 * 16;
@@ -584,7 +587,16 @@ extern "C" int h264b2_front_write_container_range(const char *h264_path, const c
         if (ev.kind == H264B2_EV_END) break;
         if (ev.kind == H264B2_EV_PICTURE) {
             wmb = ev.width_mbs; hmb = ev.height_mbs;
-            if (max_pictures <= 0 || n_pics < max_pictures) { fwrite(&ev.hdr, sizeof ev.hdr, 1, fo); fwrite(ev.block, 1, ev.block_bytes, fo); n_pics++; }
+            if (max_pictures <= 0 || n_pics < max_pictures) {
+                const size_t nmb = (size_t)wmb * hmb; const H264B2PicParams &p = ev.params;
+                fwrite(&ev.hdr, sizeof ev.hdr, 1, fo);
+                fwrite(p.mb_info, sizeof(H264B2MbInfo), nmb, fo); fwrite(p.intra_modes, 8, nmb, fo); fwrite(p.coef_offset, 4, nmb, fo);
+                if (ev.hdr.has_inter) fwrite(p.motion, sizeof(H264B2MbMotion), nmb, fo);
+                fwrite(p.weights, sizeof(H264B2Weight), (size_t)ev.hdr.n_weights, fo);
+                if (ev.hdr.n_coefs) fwrite(p.coefs, 2, ev.hdr.n_coefs, fo);
+                if (ev.hdr.custom_scaling) { fwrite(p.level_scale4, 2, 2 * 2 * 6 * 16, fo); fwrite(p.level_scale8, 2, 2 * 2 * 6 * 64, fo); }
+                n_pics++;
+            }
             h264b2_front_release(f, ev.block);
         } else if (ev.kind == H264B2_EV_OUTPUT) {
             if (max_pictures <= 0 || ev.decode_idx < max_pictures) { OutRec o; o.decode_idx = ev.decode_idx; o.pad = 0; o.sum = 0; outs.push_back(o); }

@@ -118,7 +118,9 @@ typedef struct H264B2PicParams {
     uint32_t n_coefs;              /* int16 elements in coefs[] */
     int32_t  custom_scaling;       /* 0: Flat_4x4_16 / Flat_8x8_16; 1: level_scale4/8 given */
     int32_t  reserved;
-    /* host (or device, see h264b2_submit_device) arrays */
+    /* host (or device, see h264b2_submit_device) arrays.  Alignment: the engine keeps each array's address modulo 256 when it
+     * copies it to the device and its kernels use 16-byte loads, so mb_info / motion / weights / coefs must start on 16-byte
+     * boundaries (intra_modes 8, coef_offset 4); h264b2_host_alloc and the front end's picture blocks guarantee it. */
     const H264B2MbInfo   *mb_info;     /* [width_mbs*height_mbs] */
     const uint64_t       *intra_modes; /* [n_mbs] 16 x 4 bit: Intra4x4PredMode[b] (b=luma4x4BlkIdx) or
                                           Intra8x8PredMode[b] in nibbles 0..3 */
