@@ -120,6 +120,7 @@ struct H264B2Context {
     uint8_t **d_ptrs; unsigned long long *d_sums; unsigned long long *h_sums; uint8_t **h_ptrs;
     uint8_t **h_snap[2], **h_snap_dev[2];     // mapped pinned pointer lists for k_snapshot
     uint8_t *bgr; size_t bgr_cap;             // BGR24 output staging
+    size_t bs_stride;                         // words per stream in bs
     // timing
     cudaEvent_t t0, t1;
     int timing;
@@ -220,7 +221,10 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     // tail padding: a bottom-field view clamps x to 2W-1 and may read one row past the last plane (Q4)
     CK(cudaMalloc(&c->surfaces, total + (size_t)width_mbs * 64));
     CK(cudaMemset(c->surfaces, 0, total + (size_t)width_mbs * 64));
-    CK(cudaMalloc(&c->bs, (size_t)n_streams * c->nmb * 65 * 4));
+    // per stream: 64 words of strengths per MB + 1 "any strength" word per MB; the stride is rounded to 16 bytes because k_bs
+    // writes the records with 16-byte stores (an odd macroblock count would misalign every second stream otherwise)
+    c->bs_stride = ((size_t)c->nmb * 65 + 3) & ~(size_t)3;
+    CK(cudaMalloc(&c->bs, (size_t)n_streams * c->bs_stride * 4));
     CK(cudaMalloc(&c->res, (size_t)n_streams * c->nmb * RES_MB_STRIDE * 2));
     c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 4 * MAX_GROUPS;
     {
@@ -339,7 +343,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.ls8 = p.custom_scaling ? p.level_scale8 : c->ls_flat + 2 * 2 * 6 * 16;
         d.stream_base = c->surfaces + (size_t)sids[i] * c->spp * c->frame_bytes;
         d.dst = (uint8_t *)d.stream_base + (size_t)p.dst_surface * c->frame_bytes;
-        d.bs = c->bs + (size_t)sids[i] * c->nmb * 65;
+        d.bs = c->bs + (size_t)sids[i] * c->bs_stride;
         d.res = c->res + (size_t)sids[i] * c->nmb * RES_MB_STRIDE;
         d.progress = c->progress + (size_t)sids[i] * 2 * c->hmb;
         d.frame_bytes = c->frame_bytes;
