@@ -225,7 +225,7 @@ int parse_slice_header(BitReader &br, int nal_ref_idc, int nal_unit_type, const 
     if ((pps.weighted_pred_flag && (sh.slice_type == SLICE_P || sh.slice_type == SLICE_SP)) || (pps.weighted_bipred_idc == 1 && sh.slice_type == SLICE_B)) {
         sh.luma_log2_weight_denom = (int)br.ue();                                    // pred_weight_table (H264SliceHeader.cpp:586-665)
         if (sps.ChromaArrayType != 0) sh.chroma_log2_weight_denom = (int)br.ue();
-        if (sh.luma_log2_weight_denom > 7 || sh.chroma_log2_weight_denom > 7) return -1;
+        if (sh.luma_log2_weight_denom > 30 || sh.chroma_log2_weight_denom > 30) return -1;      // (the reference has no range check; > 7 is non-conforming)
         for (int l = 0; l < (sh.slice_type == SLICE_B ? 2 : 1); l++) {
             const int n = l ? sh.num_ref_idx_l1_active_minus1 : sh.num_ref_idx_l0_active_minus1;
             for (int i = 0; i <= n; i++) {

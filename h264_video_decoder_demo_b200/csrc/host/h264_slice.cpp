@@ -135,7 +135,7 @@ struct Dec {
             const int A = nbrA(cur), B = nbrB(cur);
             const int inc = (A >= 0 && mbs[A].type != T_I_NxN) + (B >= 0 && mbs[B].type != T_I_NxN);
             if (!cb.decision(base + inc)) return 0;
-            if (cb.terminate()) return 25;
+            if (cb.terminate()) { cb.init_engine(&br); return 25; }      // REF: see macroblock_layer (I_PCM)
             int t = 1 + 12 * cb.decision(base + 3);
             if (cb.decision(base + 4)) t += 4 + 4 * cb.decision(base + 5);
             t += 2 * cb.decision(base + 6);
@@ -143,7 +143,7 @@ struct Dec {
             return t;
         }
         if (!cb.decision(base)) return 0;
-        if (cb.terminate()) return 25;
+        if (cb.terminate()) { cb.init_engine(&br); return 25; }
         int t = 1 + 12 * cb.decision(base + 1);
         if (cb.decision(base + 2)) t += 4 + 4 * cb.decision(base + 2);
         t += 2 * cb.decision(base + 3);
@@ -246,11 +246,15 @@ struct Dec {
             if (is_skip(m.type) || m.type == T_IPCM || (m.type != T_I16 && m.cbp_luma == 0 && m.cbp_chroma == 0) || m.qp_delta == 0) inc = 0;
         }
         if (!cb.decision(60 + inc)) return 0;
-        int v = 1;
-        if (cb.decision(60 + 2)) { v = 2; while (cb.decision(60 + 3)) { v++; if (v > 200) break; } }
-        return (v & 1) ? (v + 1) >> 1 : -((v + 1) >> 1);
+        int bin = cb.decision(60 + 2), binIdx = 1;
+        while (bin) { bin = cb.decision(60 + 3); binIdx++; if (binIdx > 102) return QP_DELTA_ERROR; }      // H264Cabac.cpp:4196: "too large" fails the macroblock
+        return (binIdx & 1) ? (binIdx + 1) >> 1 : -((binIdx + 1) >> 1);
     }
+    enum { QP_DELTA_ERROR = 0x7fffffff };
     // neighbouring partition of the current MB's partition at (x, y): availability, quadrant and 4x4 block in the neighbour
+    // REF: both context derivations look the neighbour's partition mode up with MbPartPredMode2(), which knows no I_PCM
+    // (H264MacroBlock.cpp:756): an available I_PCM neighbour FAILS the syntax element and with it the macroblock (H264Cabac.cpp:1466, 1736)
+    enum { MVD_ERROR = 0x7ffffffe };
     int cabac_ref_idx(int list, int x, int y) {
         int cond[2];
         for (int k = 0; k < 2; k++) {
@@ -258,6 +262,7 @@ struct Dec {
             int c = 0;
             if (n.mb >= 0) {
                 const MbT &m = mbs[n.mb];
+                if (m.type == T_IPCM) return -1;
                 const int q = (n.yW / 8) * 2 + n.xW / 8;
                 const int thr = (mbaff && mbs[cur].field == 0 && m.field == 1) ? 1 : 0;
                 const bool zero = !(m.ref_syn[list][q] > thr);
@@ -267,9 +272,9 @@ struct Dec {
             cond[k] = c;
         }
         if (!cb.decision(54 + cond[0] + 2 * cond[1])) return 0;
-        int v = 1;
-        if (cb.decision(54 + 4)) { v = 2; while (cb.decision(54 + 5)) { v++; if (v > 32) return -1; } }
-        return v;
+        int bin = cb.decision(54 + 4), binIdx = 1;
+        while (bin) { bin = cb.decision(54 + 5); binIdx++; if (binIdx > 32) return -1; }      // H264Cabac.cpp:4133
+        return binIdx;
     }
     int cabac_mvd(int list, int comp, int x, int y) {
         int sum = 0;
@@ -277,9 +282,10 @@ struct Dec {
             const Nb n = k == 0 ? nbr(cur, x - 1, y, false) : nbr(cur, x, y - 1, false);
             if (n.mb < 0) continue;
             const MbT &m = mbs[n.mb];
+            if (m.type == T_IPCM) return MVD_ERROR;
             const int q = (n.yW / 8) * 2 + n.xW / 8, b = (n.yW / 4) * 4 + n.xW / 4;
             const bool eq = (m.part_pm[q] & (1 << list)) != 0 && m.part_pm[q] != PM_DIRECT;
-            if (is_skip(m.type) || m.intra || m.type == T_IPCM || !eq) continue;
+            if (is_skip(m.type) || m.intra || !eq) continue;
             int a = abs(m.mvd[list][b][comp]);
             if (comp == 1 && mbaff) { if (mbs[cur].field == 0 && m.field == 1) a *= 2; else if (mbs[cur].field == 1 && m.field == 0) a /= 2; }
             sum += a;
@@ -291,7 +297,7 @@ struct Dec {
         while (v < 9) { if (!cb.decision(ctx)) break; v++; if (v <= 4) ctx++; }
         if (v >= 9) {
             int k = 3;
-            while (cb.bypass()) { v += 1 << k; k++; if (k >= 23) return 0x7fffffff; }
+            while (cb.bypass()) { v += 1 << k; k++; if (k >= 23) return v; }      // REF: H264Cabac.cpp:4048 returns "success" here: no suffix, no sign
             while (k--) v += cb.bypass() << k;
         }
         return cb.bypass() ? -v : v;
@@ -374,7 +380,11 @@ struct Dec {
                 ctx = absBase + 5 + std::min(gtMax, gt1);
                 v = 1;
                 while (v < 14 && cb.decision(ctx)) v++;
-                if (v >= 14) { int e = 0; while (cb.bypass()) { v += 1 << e; e++; if (e > 24) break; } while (e--) v += cb.bypass() << e; }
+                if (v >= 14) {
+                    int e = 0; bool cut = false;
+                    while (cb.bypass()) { v += 1 << e; e++; if (e >= 18) { cut = true; break; } }      // REF: H264Cabac.cpp:4905 stops without the suffix bits
+                    if (!cut) while (e--) v += cb.bypass() << e;
+                }
             }
             const int a = v + 1;
             if (a == 1) eq1++; else gt1++;
@@ -598,7 +608,10 @@ struct Dec {
                 int x, y, w, h; part_rect(m, p, 0, &x, &y, &w, &h);
                 const int pm = m.part_pm[(y / 8) * 2 + x / 8];
                 if (pm & (1 << list)) {
-                    const int dx = read_mvd(list, 0, x, y), dy = read_mvd(list, 1, x, y);
+                    const int dx = read_mvd(list, 0, x, y);
+                    if (dx == MVD_ERROR) return -1;
+                    const int dy = read_mvd(list, 1, x, y);
+                    if (dy == MVD_ERROR) return -1;
                     for (int yy = y; yy < y + h; yy += 4) for (int xx = x; xx < x + w; xx += 4) { m.mvd[list][(yy / 4) * 4 + xx / 4][0] = (int16_t)dx; m.mvd[list][(yy / 4) * 4 + xx / 4][1] = (int16_t)dy; }
                 }
             }
@@ -636,7 +649,10 @@ struct Dec {
                 if (!m.sub_direct[p] && (m.part_pm[p] & (1 << list)))
                     for (int s = 0; s < nsub[p]; s++) {
                         int x, y, w, h; part_rect(m, p, s, &x, &y, &w, &h);
-                        const int dx = read_mvd(list, 0, x, y), dy = read_mvd(list, 1, x, y);
+                        const int dx = read_mvd(list, 0, x, y);
+                        if (dx == MVD_ERROR) return -1;
+                        const int dy = read_mvd(list, 1, x, y);
+                        if (dy == MVD_ERROR) return -1;
                         for (int yy = y; yy < y + h; yy += 4) for (int xx = x; xx < x + w; xx += 4) { m.mvd[list][(yy / 4) * 4 + xx / 4][0] = (int16_t)dx; m.mvd[list][(yy / 4) * 4 + xx / 4][1] = (int16_t)dy; }
                     }
         *noSub8x8 = 1;
@@ -644,8 +660,10 @@ struct Dec {
             if (!m.sub_direct[p]) { if (nsub[p] > 1) *noSub8x8 = 0; }
             else if (!sh.sps.direct_8x8_inference_flag) *noSub8x8 = 0;
         }
-        // (the reference rejects B sub-macroblock types 4..12 at this point, MB:1061-1069, and then loses bitstream
-        //  synchronisation; that failure mode is not reproduced — such streams are parsed as H.264 specifies)
+        // REF: after sub_mb_pred() the reference looks the sub-macroblock types up again and accepts only 0..3 in B macroblocks
+        // (H264MacroBlock.cpp:1061-1069): B_8x8 with an 8x4 / 4x8 / 4x4 sub-macroblock FAILS macroblock_layer() here — no
+        // coded_block_pattern, no residual, QPY stays 0 — and parsing goes on from this bit position (SD:380-384).  Reproduced.
+        if (isB) for (int p = 0; p < 4; p++) if (!m.sub_direct[p] && m.sub_shape[p] != 0) return -1;
         return 0;
     }
 
@@ -663,10 +681,11 @@ struct Dec {
         else return -1;
         if (it >= 0) classify_intra(m, it); else classify_inter(m, st, mb_type);
         if (m.type == T_IPCM) {
-            if (cabac) { /* 9.3.1.2: the arithmetic decoder stopped at a byte-aligned position after the terminate bin */ }
+            // REF (CABAC): the reference re-initialises the arithmetic decoder right after the I_PCM bin — 9 bits BEFORE the alignment
+            // bits and the samples (H264Cabac.cpp:3233-3238) instead of after them (9.3.1.2) — and does not initialise it again
+            // afterwards; done in cabac_intra_mb_type().  The samples are then read from wherever that leaves the bitstream.
             while (!br.aligned()) br.u1();
             for (int i = 0; i < 384; i++) pcm[i] = (int16_t)br.u(8);
-            if (cabac) cb.init_engine(&br);
         } else {
             int noSub8x8 = 1;
             if (m.type == T_P8x8 || m.type == T_P8x8ref0 || m.type == T_B8x8) { if (sub_mb_pred(m, &noSub8x8)) return -1; }
@@ -694,6 +713,7 @@ struct Dec {
             }
             if (m.cbp_luma > 0 || m.cbp_chroma > 0 || m.type == T_I16) {
                 int d = cabac ? cabac_mb_qp_delta() : br.se();
+                if (d == QP_DELTA_ERROR) return -1;
                 m.qp_delta = (int8_t)std::max(-128, std::min(127, d));
                 if (residual()) return -1;
                 residual_ok = true;
@@ -906,7 +926,10 @@ struct Dec {
         MbT &m = mbs[cur];
         dc_valid = false;
         H264B2MbMotion &M = mot[cur];
-        memset(M.ref_surf, -1, sizeof M.ref_surf); memset(M.ref_ident, -1, sizeof M.ref_ident);
+        memset(M.ref_surf, -1, sizeof M.ref_surf);
+        // m_RefIdxLX are 0 until a partition is derived (memset of m_mbs): a macroblock whose derivation stops early still reports the
+        // identity of RefPicListX[0] for the partitions it never reached (oracle/ref_harness.cpp reads refIdx >= 0 whatever predFlag is)
+        for (int l = 0; l < 2; l++) for (int q = 0; q < 4; q++) M.ref_ident[l][q] = (int8_t)S.list[l][0];
         F.has_inter = 1;
         const bool direct16 = m.type == T_BSKIP || m.type == T_BDIRECT;
         const bool is8x8 = m.type == T_P8x8 || m.type == T_P8x8ref0 || m.type == T_B8x8;
@@ -1061,7 +1084,11 @@ struct Dec {
     int run() {
         const int st = sh.slice_type;
         F.slice_number = ++S.slice_number;
-        if (cabac) { while (!br.aligned()) br.u1(); cb.init_contexts(st, sh.cabac_init_idc, sh.SliceQPY); cb.init_engine(&br); }
+        if (cabac) {
+            if ((unsigned)sh.cabac_init_idc > 2) return -1;      // non-conforming (the reference goes on with uninitialised contexts, H264Cabac.cpp:41)
+            while (!br.aligned()) br.u1();
+            cb.init_contexts(st, sh.cabac_init_idc, sh.SliceQPY); cb.init_engine(&br);
+        }
         if (!mbaff) F.mb_field = sh.field_pic_flag;
         cur = sh.first_mb_in_slice * (1 + mbaff);
         F.qp_prev = sh.SliceQPY;

@@ -521,3 +521,54 @@ class Stream:
                 n_ref_done += 1
                 ref_pocs.append(poc)
         return bytes(self.out)
+
+
+def random_cabac_stream(seed, kind="I", wmb=6, hmb=5, n_pics=4, nbytes=300, t8x8=False):
+    """CABAC pictures whose slice DATA is random bytes: valid parameter sets and slice headers, then noise for the arithmetic decoder.
+    Whatever syntax the UNMODIFIED reference decodes from the noise (macroblock types incl. I_PCM, sub-partitions, the B sub-types it
+    rejects, over-long mb_qp_delta / level / mvd codes, slices that run out of data) is the golden answer — error paths included.
+    kind: "I" (intra pictures only), "P" (one reference, ref_idx never coded) or "B" (I P B P B, one reference per list)."""
+    b_mode = kind == "B"
+    st = Stream(seed=seed, wmb=wmb, hmb=hmb, t8x8=t8x8, n_refs=2 if b_mode else 1, poc_type=0 if b_mode else 2, bframes=b_mode)
+    rng = st.rng
+    out = bytearray(st.sps())
+    b = Bits()
+    b.ue(0); b.ue(0); b.u(1, 1); b.u(1, 0); b.ue(0); b.ue(0); b.ue(0)
+    b.u(1, 0); b.u(2, int(rng.choice([0, 2])) if b_mode else 0)
+    b.se(0); b.se(0); b.se(0); b.u(1, 1); b.u(1, 0); b.u(1, 0)
+    b.u(1, 1 if t8x8 else 0); b.u(1, 0); b.se(0)
+    b.trailing()
+    out += nal(3, 8, b.rbsp())
+    if b_mode:
+        plan = [("I", 0, True), ("P", 4, True), ("B", 2, False), ("P", 8, True), ("B", 6, False)][:n_pics + 1]
+    elif kind == "P":
+        plan = [("I", 0, True)] + [("P", 2 * i, True) for i in range(1, n_pics)]
+    else:
+        plan = [("I", 2 * i, True) for i in range(n_pics)]
+    n_ref = 0
+    for p, (k, poc, is_ref) in enumerate(plan):
+        b = Bits()
+        b.ue(0); b.ue({"I": 2, "P": 0, "B": 1}[k]); b.ue(0); b.u(8, n_ref & 255)
+        if p == 0:
+            b.ue(0)
+        if b_mode:
+            b.u(8, poc & 255)
+        if k == "B":
+            b.u(1, 1)                      # direct_spatial_mv_pred_flag
+        if k != "I":
+            b.u(1, 0); b.u(1, 0)           # no num_ref_idx override, no modification of list 0
+        if k == "B":
+            b.u(1, 0)
+        if p == 0:
+            b.u(1, 0); b.u(1, 0)
+        elif is_ref:
+            b.u(1, 0)
+        if k != "I":
+            b.ue(int(rng.integers(0, 3)))  # cabac_init_idc
+        b.se(int(rng.integers(-6, 7))); b.ue(0); b.se(0); b.se(0)
+        while len(b.b) % 8:
+            b.b.append(1)                  # cabac_alignment_one_bit
+        out += nal(1 if is_ref else 0, 5 if p == 0 else 1, b.rbsp() + rng.integers(0, 256, nbytes, dtype=np.uint8).tobytes() + b"\x80")
+        if is_ref:
+            n_ref += 1
+    return bytes(out)
