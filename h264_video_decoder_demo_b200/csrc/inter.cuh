@@ -209,18 +209,10 @@ __device__ __forceinline__ int weigh(const H264B2Weight &w, int c, int have0, in
     return ld >= 1 ? clip255(((p * ww + (1 << (ld - 1))) >> ld) + oo) : clip255(p * ww + oo);
 }
 
-// grid: (ceil(n_mbs / 8), n_pics); block: 128 threads = 4 warps; warp w = 4x4-block row `by` of 8 consecutive
-// macroblock addresses, lane = (mb_in_group << 2) | bx.
-#ifndef INTER_MIN_BLOCKS
-#define INTER_MIN_BLOCKS 5
-#endif
-__global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *pics) {
-    const PicDev &P = pics[blockIdx.y];
-    const int lane = threadIdx.x & 31, by4 = threadIdx.x >> 5, bx4 = lane & 3;
-    const int a = blockIdx.x * 8 + (lane >> 2);
-    if (!P.motion || a >= P.wmb * P.hmb) return;
-    const H264B2MbInfo I = P.info[a];
-    if (I.mb_class != H264B2_MB_INTER) return;
+// Generic path: ONE 4x4 luma block (raster slot r = by4 * 4 + bx4) of inter macroblock `a` with its 2x2 Cb / Cr samples.
+// Used by k_inter (inter_quad.cuh) for macroblocks whose 8x8 quadrants carry more than one motion vector.
+__device__ __noinline__ void inter_block_generic(const PicDev &P, int a, const H264B2MbInfo &I, int r4) {
+    const int by4 = r4 >> 2, bx4 = r4 & 3;
     const int field = P.mbaff && (I.flags & H264B2_MBF_FIELD);
     const int ys = field ? 2 : 1;
     int x0, y0;
