@@ -100,7 +100,9 @@ struct H264B2Context {
     int *progress;            // [n_streams][2][hmb] then DESC_RING*2 tickets
     size_t progress_ints;
     int16_t *ls_flat;         // ls4 [2][2][6][16] then ls8 [2][2][6][64]
-    cudaStream_t st, st_h2d, st_d2h;
+    cudaStream_t st, st_h2d, st_h2d2, st_d2h;
+    int h2d_streams;                          // 1 or 2 copy streams for host-array submits (H264B2_H2D_STREAMS)
+    size_t d2h_chunk;                         // read-backs into adjacent host memory are merged into copies of at most this size
     // A batch is cut into `groups` picture groups whose kernel sequences run on separate streams, forked from and
     // joined back into `st`: the latency-bound wavefront kernels of one group overlap the issue-bound kernels
     // (and the wavefronts) of the others.
@@ -113,7 +115,7 @@ struct H264B2Context {
     int desc_next;
     // host-submit staging: device arena slots
     uint8_t *arena[NSLOT]; size_t arena_cap[NSLOT];
-    cudaEvent_t h2d_done[NSLOT], compute_done[NSLOT];
+    cudaEvent_t h2d_done[NSLOT], h2d_done2[NSLOT], compute_done[NSLOT];
     int slot_next;
     // read-back staging
     uint8_t *out_stage[2]; size_t out_cap[2]; cudaEvent_t out_ready[2], out_done[2]; int out_next;
@@ -238,6 +240,9 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaMalloc(&c->progress, c->progress_ints * 4));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->st_h2d2, cudaStreamNonBlocking));
+    { const char *e = getenv("H264B2_H2D_STREAMS"); c->h2d_streams = (e && atoi(e) == 2) ? 2 : 1; }      // measured on the B200 box: 2 queues 10.8k frames/s e2e, 1 queue 11.1k
+    { const char *e = getenv("H264B2_D2H_CHUNK_MB"); c->d2h_chunk = (size_t)(e && atoi(e) > 0 ? atoi(e) : 1) << 20; }      // default: one transfer per picture (64 MB merged transfers measured 6 % slower with H2D running)
     CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < MAX_GROUPS; i++) {
         CK(cudaStreamCreateWithFlags(&c->st_g[i], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
@@ -253,7 +258,7 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     }
     CK(cudaMalloc(&c->d_desc, sizeof(PicDev) * n_streams * DESC_RING));
     for (int i = 0; i < DESC_RING; i++) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
-    for (int i = 0; i < NSLOT; i++) { CK(cudaEventCreateWithFlags(&c->h2d_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming)); }
+    for (int i = 0; i < NSLOT; i++) { CK(cudaEventCreateWithFlags(&c->h2d_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->h2d_done2[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming)); }
     for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->out_ready[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming)); }
     CK(cudaMalloc(&c->d_ptrs, sizeof(uint8_t *) * n_streams));
     CK(cudaMalloc(&c->d_sums, 8 * n_streams));
@@ -274,14 +279,14 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     cudaDeviceSynchronize();
     if (c->bgr) cudaFree(c->bgr);
     cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_snap[0]); cudaFreeHost(c->h_snap[1]);
-    for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->compute_done[i]); }
+    for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->h2d_done2[i]); cudaEventDestroy(c->compute_done[i]); }
     for (int i = 0; i < 2; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
     for (int i = 0; i < DESC_RING; i++) cudaEventDestroy(c->desc_ev[i]);
     cudaFree(c->d_ptrs); cudaFree(c->d_sums); cudaFreeHost(c->h_sums); cudaFreeHost(c->h_ptrs);
     for (int i = 0; i < EV_POOL; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     free(c->ev);
     cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
-    cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_d2h);
+    cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_h2d2); cudaStreamDestroy(c->st_d2h);
     for (int i = 0; i < MAX_GROUPS; i++) { cudaStreamDestroy(c->st_g[i]); cudaStreamDestroy(c->st_side[i]); cudaEventDestroy(c->join_ev[i]); cudaEventDestroy(c->side_fork[i]); cudaEventDestroy(c->side_join[i]); }
     cudaEventDestroy(c->fork_ev);
     delete c;
@@ -465,17 +470,20 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
         CK(cudaMalloc(&c->arena[slot], c->arena_cap[slot]));
     }
     CK(cudaStreamWaitEvent(c->st_h2d, c->compute_done[slot], 0));
+    if (c->h2d_streams > 1) CK(cudaStreamWaitEvent(c->st_h2d2, c->compute_done[slot], 0));
     trace_mark(c, 0, c->st_h2d);
     // copy: merge spans that are adjacent in host memory (same relative alignment kept)
     size_t off = 0;
     size_t i = 0;
+    unsigned ncopy = 0;
     while (i < spans.size()) {
         size_t j = i;
         const uint8_t *lo = spans[i].p; const uint8_t *hi = lo + spans[i].n;
         while (j + 1 < spans.size() && spans[j + 1].p >= hi && (size_t)(spans[j + 1].p - hi) <= 64) { j++; hi = spans[j].p + spans[j].n; }
         // keep the host address's offset within 256 so that every array keeps its natural alignment
         off = al256(off) + ((size_t)(uintptr_t)lo & 255);
-        CK(cudaMemcpyAsync(c->arena[slot] + off, lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, c->st_h2d));
+        // picture-sized DMAs leave gaps on one copy queue (profiles/r01_pcie_probe.txt): alternate between two
+        CK(cudaMemcpyAsync(c->arena[slot] + off, lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, (c->h2d_streams > 1 && (ncopy++ & 1)) ? c->st_h2d2 : c->st_h2d));
         for (size_t k = i; k <= j; k++) *spans[k].slot = c->arena[slot] + off + (spans[k].p - lo);
         off += (size_t)(hi - lo);
         i = j + 1;
@@ -483,6 +491,7 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
     CK(cudaEventRecord(c->h2d_done[slot], c->st_h2d));
     trace_mark(c, 1, c->st_h2d);
     CK(cudaStreamWaitEvent(c->st, c->h2d_done[slot], 0));
+    if (c->h2d_streams > 1) { CK(cudaEventRecord(c->h2d_done2[slot], c->st_h2d2)); CK(cudaStreamWaitEvent(c->st, c->h2d_done2[slot], 0)); }
     trace_mark(c, 2, c->st);
     r = launch_batch(c, n_pics, sids, dev.data());
     if (r) return r;
@@ -504,7 +513,7 @@ extern "C" int h264b2_surface_ptr(H264B2Context *c, int sid, int surface, void *
 extern "C" int h264b2_sync(H264B2Context *c) {
     if (!c) return fail(-1, "null context");
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->st_h2d)); CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_d2h));
+    CK(cudaStreamSynchronize(c->st_h2d)); CK(cudaStreamSynchronize(c->st_h2d2)); CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_d2h));
     trace_dump(c);
     return 0;
 }
@@ -544,8 +553,14 @@ extern "C" int h264b2_read_pictures_async(H264B2Context *c, int n, const int32_t
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->out_ready[s], c->st));
     CK(cudaStreamWaitEvent(c->st_d2h, c->out_ready[s], 0));
-    for (int i = 0; i < n; i++)
-        CK(cudaMemcpyAsync(host[i], c->out_stage[s] + (size_t)i * c->frame_bytes, c->frame_bytes, cudaMemcpyDeviceToHost, c->st_d2h));
+    // the staging buffer is contiguous: destinations that are adjacent in host memory leave as ONE transfer (bounded chunks)
+    const int per = (int)std::max<size_t>(1, c->d2h_chunk / c->frame_bytes);
+    for (int i = 0; i < n; ) {
+        int j = i + 1;
+        while (j < n && j - i < per && host[j] == host[j - 1] + c->frame_bytes) j++;
+        CK(cudaMemcpyAsync(host[i], c->out_stage[s] + (size_t)i * c->frame_bytes, (size_t)(j - i) * c->frame_bytes, cudaMemcpyDeviceToHost, c->st_d2h));
+        i = j;
+    }
     CK(cudaEventRecord(c->out_done[s], c->st_d2h));
     return 0;
 }
@@ -614,7 +629,7 @@ extern "C" int h264b2_timer_start(H264B2Context *c) {
 extern "C" int h264b2_timer_stop(H264B2Context *c, float *ms) {
     if (!c || !ms) return fail(-1, "bad argument");
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->st_h2d));
+    CK(cudaStreamSynchronize(c->st_h2d)); CK(cudaStreamSynchronize(c->st_h2d2));
     for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(c->st, c->out_done[i], 0));   // t1 also covers pending read-backs
     CK(cudaEventRecord(c->t1, c->st));
     CK(cudaEventSynchronize(c->t1));
