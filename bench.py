@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-mode", default="full", choices=["full", "h2d", "d2h"], help="diagnostic: which PCIe legs the e2e loop includes")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--host-layout", default="batch", choices=["batch", "shared"], help="e2e: picture blocks of a submit back to back in pinned memory (one DMA per batch) or one block per distinct picture")
+    ap.add_argument("--dense-coefs", action="store_true", help="e2e: send plain arrays (dense int16 levels, full motion records) instead of the packed transport")
     ap.add_argument("--no-bitstream", action="store_true", help="skip the Annex-B-in / frames-out pipeline measurement")
     ap.add_argument("--bitstream-streams", type=int, default=32, help="streams per GPU of the Annex-B pipeline measurement")
     ap.add_argument("--bitstream-threads", type=int, default=0, help="parser threads (0 = usable host cores / ranks)")
@@ -236,7 +238,45 @@ def main():
         pinned[:] = np.frombuffer(raw, dtype=np.uint8)
         del raw
         rpv = replay.parse_replay(pinned, path, args.max_pictures)
-        variants.append({"rp": rpv, "host_params": [replay.pic_params(rpv, pic) for pic in rpv.pictures], "rs": None})
+        # what the host stage hands to h264b2_submit: one page-locked block per picture (the layout of the front end's picture
+        # blocks: arrays back to back, 64-byte aligned -> ONE DMA per picture), coefficients packed by h264b2_pack_coefs
+        blobs, host_params = None, None
+        if not args.dense_coefs:
+            names = ("mb_info", "intra_modes", "coef_offset", "motion", "weights", "level_scale4", "level_scale8")
+            al = lambda n: (n + 63) & ~63
+            cb = lambda pic: int(eng.lib.h264b2_pack_coefs_bound(len(pic.coefs)))
+            mb_ = lambda pic: int(eng.lib.h264b2_pack_coefs_bound(pic.motion.size * 76)) if pic.motion is not None else 0
+            bound = sum(sum(al(getattr(pic, k).nbytes) for k in names if getattr(pic, k) is not None) + al(cb(pic)) + al(mb_(pic)) + 64 for pic in rpv.pictures)
+            store, blobs, mblobs, host_params, o = eng.pinned_array(bound), [], [], [], 0
+            o += (-store.ctypes.data) % 64
+            extents = []
+            for pic in rpv.pictures:
+                ptrs, o0, mblob = {}, o, None
+                for k in names:
+                    a = getattr(pic, k)
+                    if a is None or not a.size:
+                        continue
+                    if k == "motion":
+                        if not pic.has_inter:
+                            continue
+                        mblob = engine.pack_motion(a, store[o:o + mb_(pic)])
+                        ptrs[k] = mblob.ctypes.data
+                        o += al(mblob.size)
+                        continue
+                    store[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+                    ptrs[k] = store.ctypes.data + o
+                    o += al(a.nbytes)
+                b = engine.pack_coefs(pic.coefs, store[o:o + cb(pic)])
+                o += al(b.size)
+                blobs.append(b)
+                mblobs.append(mblob)
+                ptrs["coefs"] = b.ctypes.data
+                host_params.append(replay.pic_params(rpv, pic, ptrs=ptrs, packed_blob=b, packed_motion=mblob))
+                extents.append((o0, o - o0, ptrs))
+        else:
+            host_params = [replay.pic_params(rpv, pic) for pic in rpv.pictures]
+        variants.append({"rp": rpv, "host_params": host_params, "_store": store if blobs else None, "extents": extents if blobs else None, "blobs": blobs, "mblobs": mblobs if blobs else None,
+                         "host_bytes": [e[1] for e in extents] if blobs else [pic.nbytes() for pic in rpv.pictures], "rs": None})
     sids = list(range(S))
     var_of = [s % len(variants) for s in sids]
     rs = []
@@ -254,7 +294,38 @@ def main():
         return i % len(variants[var_of[s]]["rp"].pictures)
 
     batches = [eng.prepare(sids, [rs[s].params[pic_of(s, i)] for s in sids]) for i in range(npic)]
-    host_batches = [eng.prepare(sids, [variants[var_of[s]]["host_params"][pic_of(s, i)] for s in sids]) for i in range(npic)]
+    # Host layout of the e2e leg.  "batch": the picture blocks of one submit lie back to back in page-locked memory (a batch arena,
+    # as the host stage's allocator hands them out), so h264b2_submit moves a batch in ONE DMA and the read-back of a batch is
+    # one DMA too — picture-sized transfers cost 35 % of the link when both directions run (profiles/r01_pcie_probe2.txt).
+    # "shared": one block per distinct picture, one DMA per picture (also the fallback when host memory is short).
+    host_layout, arena = "shared", None
+    if not args.dense_coefs and not args.no_e2e and args.host_layout == "batch":
+        need = sum(variants[var_of[s]]["extents"][pic_of(s, i)][1] for s in sids for i in range(npic)) + 4096
+        avail = int(re.search(r"MemAvailable:\s+(\d+)", open("/proc/meminfo").read()).group(1)) * 1024
+        if avail > 3 * need:
+            host_layout = "batch"
+            arena = eng.pinned_array(need)
+            o = (-arena.ctypes.data) % 64
+            host_batches = []
+            for i in range(npic):
+                plist = []
+                for s in sids:
+                    v = variants[var_of[s]]
+                    k = pic_of(s, i)
+                    o0, ln, ptrs = v["extents"][k]
+                    arena[o:o + ln] = v["_store"][o0:o0 + ln]
+                    delta = arena.ctypes.data + o - (v["_store"].ctypes.data + o0)
+                    blob, mblob = v["blobs"][k], v["mblobs"][k]
+                    pp = replay.pic_params(v["rp"], v["rp"].pictures[k], ptrs={n_: a_ + delta for n_, a_ in ptrs.items()}, packed_blob=blob, packed_motion=mblob)
+                    if pp.packed & 1:
+                        pp.coefs = blob.ctypes.data + delta
+                    if pp.packed & 2:
+                        pp.motion = mblob.ctypes.data + delta
+                    plist.append(pp)
+                    o += ln
+                host_batches.append(eng.prepare(sids, plist))
+    if host_layout == "shared":
+        host_batches = [eng.prepare(sids, [variants[var_of[s]]["host_params"][pic_of(s, i)] for s in sids]) for i in range(npic)]
     dst = [[variants[var_of[s]]["rp"].pictures[pic_of(s, i)].dst_surface for s in sids] for i in range(npic)]
     want = [[variants[var_of[s]]["rp"].pictures[pic_of(s, i)].sum_post for s in sids] for i in range(npic)]
 
@@ -361,7 +432,8 @@ def main():
         e2e_dev_ms = eng.timer_stop()
         e2e_kt = eng.kernel_times()
         e2e = {"value": round(S * npic * args.e2e_steps * world / t1, 1), "unit": UNIT,
-               "h2d_bytes_per_step": int(sum(variants[var_of[s]]["rp"].pictures[pic_of(s, i)].nbytes() for s in sids for i in range(npic))),
+               "h2d_bytes_per_step": int(sum(variants[var_of[s]]["host_bytes"][pic_of(s, i)] for s in sids for i in range(npic))),
+               "host_layout": host_layout, "arrays": "plain (dense int16 levels, 152-byte motion records)" if args.dense_coefs else "packed levels and motion records (h264b2_pack_coefs / h264b2_pack_motion)",
                "d2h_bytes_per_step": int(npic * S * eng.frame_bytes),
                "steps": args.e2e_steps, "device_ms_per_step": round(e2e_dev_ms / args.e2e_steps, 1),
                "kernel_ms_per_step": {k: round(v["ms"] / args.e2e_steps, 1) for k, v in e2e_kt.items()}, "timing": "host wall clock around submit+read-back of every picture, synchronised on both sides, max over ranks"}

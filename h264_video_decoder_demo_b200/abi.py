@@ -6,7 +6,7 @@ against the compiled library.
 import ctypes as C
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # macroblock classes (H264B2_MB_*)
 MB_NA, MB_I4x4, MB_I8x8, MB_I16x16, MB_IPCM, MB_INTER = range(6)
@@ -49,7 +49,7 @@ class PicParams(C.Structure):
         ("width_mbs", C.c_int32), ("height_mbs", C.c_int32), ("mbaff_frame_flag", C.c_int32),
         ("chroma_qp_offset", C.c_int32 * 2), ("dst_surface", C.c_int32), ("clear_surface", C.c_int32),
         ("has_inter", C.c_int32), ("deblock_enable", C.c_int32), ("deblock_stop_mb", C.c_int32),
-        ("n_weights", C.c_int32), ("n_coefs", C.c_uint32), ("custom_scaling", C.c_int32), ("reserved", C.c_int32),
+        ("n_weights", C.c_int32), ("n_coefs", C.c_uint32), ("custom_scaling", C.c_int32), ("packed", C.c_int32),
         ("mb_info", C.c_void_p), ("intra_modes", C.c_void_p), ("coef_offset", C.c_void_p), ("motion", C.c_void_p),
         ("weights", C.c_void_p), ("coefs", C.c_void_p), ("level_scale4", C.c_void_p), ("level_scale8", C.c_void_p),
     ]

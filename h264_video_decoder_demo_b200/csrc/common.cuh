@@ -15,6 +15,8 @@ struct alignas(16) PicDev {
     const H264B2MbMotion *motion;      // nullptr when the picture has no inter MB
     const H264B2Weight   *weights;
     const int16_t        *coefs;
+    const uint32_t       *packed;      // packed coefficient blob (h264b2_pack_coefs) that k_expand turns into coefs[], or nullptr
+    const uint32_t       *packed_motion; // packed motion blob (h264b2_pack_motion) that k_expand + k_unmotion turn into motion[], or nullptr
     const int16_t        *ls4;         // [2 inter][2 field scan][6][16] LevelScale4x4 in list order (PB:4852)
     const int16_t        *ls8;         // [2][2][6][64]
     uint8_t              *dst;         // Y plane of the destination surface; Cb = dst + W*H, Cr = Cb + W*H/4
@@ -27,7 +29,7 @@ struct alignas(16) PicDev {
     int deblock_enable, deblock_stop;
     int n_weights;
     int generic;                       // 1: MBAFF picture (or wider than 256 MBs): literal per-sample-line paths; 0: progressive fast paths
-    int pad_[2];                       // sizeof(PicDev) is a multiple of 16: the batch prologue copies it as uint4
+    int pad_[3];                       // sizeof(PicDev) is a multiple of 16: the batch prologue copies it as uint4
 };
 static_assert(sizeof(PicDev) % 16 == 0, "PicDev must be a multiple of 16 bytes");
 

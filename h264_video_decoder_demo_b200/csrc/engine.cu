@@ -60,6 +60,89 @@ __global__ void k_snapshot(const uint8_t *const *src, uint8_t *dst, size_t n16) 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
 }
 
+// pull host arrays into the device arena with SM loads over PCIe (optional submit path, H264B2_H2D_ZEROCOPY=<ctas>): the
+// copy engines then only carry the read-back.  src and dst share their offset modulo 16.
+struct PullDesc { const uint8_t *src; uint8_t *dst; size_t bytes; };
+__global__ void __launch_bounds__(256) k_pull(const PullDesc *list, int n) {
+    for (int e = 0; e < n; e++) {
+        const PullDesc d = list[e];
+        const size_t head = (16 - ((uintptr_t)d.src & 15)) & 15;
+        const size_t h = head < d.bytes ? head : d.bytes;
+        const size_t n16 = (d.bytes - h) / 16, tail = d.bytes - h - n16 * 16;
+        if (blockIdx.x == 0 && threadIdx.x < h) d.dst[threadIdx.x] = __ldcv(d.src + threadIdx.x);
+        if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x - 32 < tail) d.dst[h + n16 * 16 + threadIdx.x - 32] = __ldcv(d.src + h + n16 * 16 + threadIdx.x - 32);
+        const uint4 *s = (const uint4 *)(d.src + h);
+        uint4 *o = (uint4 *)(d.dst + h);
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n16; i += 4 * stride) {
+            const uint4 a = __ldcv(s + i), b = __ldcv(s + i + stride), c2 = __ldcv(s + i + 2 * stride), d2 = __ldcv(s + i + 3 * stride);
+            o[i] = a; o[i + stride] = b; o[i + 2 * stride] = c2; o[i + 3 * stride] = d2;
+        }
+        for (; i < n16; i += stride) o[i] = __ldcv(s + i);
+    }
+}
+
+// drain the staging buffer into page-locked HOST memory with SM stores over PCIe (optional read-back path: no copy-engine
+// descriptor per picture; a few persistent CTAs are enough, the stores are posted)
+__global__ void __launch_bounds__(256) k_drain(const uint8_t *stage, uint8_t *const *dst, size_t n16, int n) {
+    for (int p = 0; p < n; p++) {
+        const uint4 *s = (const uint4 *)stage + (size_t)p * n16;
+        uint4 *d = (uint4 *)dst[p];
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d[i] = __ldcs(s + i);
+    }
+}
+
+// ---- packed coefficient transport (include/h264_recon_b200.h: h264b2_pack_coefs).  Entropy-decoded residuals are sparse
+// (5.7 % non-zero in the bundled 1080p streams), so the host may send, instead of the dense int16 array, one 16-bit
+// significance map per 16-coefficient chunk plus the non-zero levels; k_expand rebuilds the dense array in HBM before
+// k_residual runs.  Blob: uint32 {magic, n_chunks, n_values, total_bytes}, uint32 base[ceil(n_chunks/32)] (first value
+// index of each group of 32 chunks), uint16 map[n_chunks rounded up to even], int16 values[n_values].
+#define H264B2_PACK_MAGIC 0x4B503248u
+__global__ void __launch_bounds__(256) k_expand(const PicDev *pics) {
+    const PicDev &P = pics[blockIdx.y];
+    const uint32_t *blob = blockIdx.z ? P.packed_motion : P.packed;         // grid.z: 0 = coefficients, 1 = motion records
+    if (!blob) return;
+    int16_t *out = blockIdx.z ? (int16_t *)P.motion : (int16_t *)P.coefs;
+    const uint32_t n_chunks = blob[1], n_groups = (n_chunks + 31) >> 5;
+    const uint32_t *base = blob + 4;
+    const uint16_t *map = (const uint16_t *)(base + n_groups);
+    const int16_t *values = (const int16_t *)(map + ((n_chunks + 1) & ~1u));
+    const int lane = threadIdx.x & 31;
+    for (uint32_t g = blockIdx.x * 8 + (threadIdx.x >> 5); g < n_groups; g += gridDim.x * 8) {
+        const uint32_t chunk = g * 32 + lane;
+        const uint32_t bm = chunk < n_chunks ? map[chunk] : 0u;
+        const int pc = __popc(bm);
+        int incl = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        const int16_t *v = values + base[g] + (incl - pc);
+        if (chunk < n_chunks) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t lo = (bm >> (2 * i)) & 1u ? (uint16_t)v[__popc(bm & ((1u << (2 * i)) - 1))] : 0u;
+                const uint32_t hi = (bm >> (2 * i + 1)) & 1u ? (uint16_t)v[__popc(bm & ((1u << (2 * i + 1)) - 1))] : 0u;
+                w[i] = lo | (hi << 16);
+            }
+            uint4 *dst = (uint4 *)(out + (size_t)chunk * 16);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]); dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
+}
+
+// undo the XOR chain h264b2_pack_motion put on the 16 vectors of each list (thread = one list of one macroblock)
+__global__ void __launch_bounds__(256) k_unmotion(const PicDev *pics) {
+    const PicDev &P = pics[blockIdx.y];
+    if (!P.packed_motion) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.wmb * P.hmb * 2) return;
+    uint2 *w = (uint2 *)((uint8_t *)P.motion + (size_t)(t >> 1) * sizeof(H264B2MbMotion) + (t & 1) * 64);     // records are 8-byte aligned
+    uint32_t prev = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { uint2 v = w[i]; v.x ^= prev; v.y ^= v.x; prev = v.y; w[i] = v; }
+}
+
 // YUV420P -> BGR24 (the reference's integer BT.601 conversion, H264PictureBase.cpp:440-468 / FlipLines :471-498).
 // One thread = 4 horizontally adjacent pixels: one 32-bit luma load, 12 output bytes as three 32-bit stores.
 __global__ void k_bgr24(const uint8_t *i420, int W, int H, uint8_t *bgr, int width_bytes, int flip) {
@@ -89,7 +172,7 @@ __global__ void k_bgr24(const uint8_t *i420, int W, int H, uint8_t *bgr, int wid
 }
 
 // ------------------------------------------------------------------ context
-enum { NSLOT = 3, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 6, MAX_GROUPS = 8 };
+enum { NSLOT = H264B2_SUBMIT_DEPTH, NOUT = 4, DESC_RING = 8, EV_POOL = 1 << 17, KCLASSES = 6, MAX_GROUPS = 8 };
 
 struct H264B2Context {
     int device, n_streams, spp, wmb, hmb, nmb;
@@ -102,6 +185,8 @@ struct H264B2Context {
     int16_t *ls_flat;         // ls4 [2][2][6][16] then ls8 [2][2][6][64]
     cudaStream_t st, st_h2d, st_h2d2, st_d2h;
     int h2d_streams;                          // 1 or 2 copy streams for host-array submits (H264B2_H2D_STREAMS)
+    int d2h_zerocopy, d2h_ctas;               // H264B2_D2H_ZEROCOPY=<ctas>: read-backs leave through k_drain instead of the copy engine
+    size_t h2d_last_bytes; unsigned h2d_last_copies;     // shape of the last host-array submit (drives the read-back policy)
     size_t d2h_chunk;                         // read-backs into adjacent host memory are merged into copies of at most this size
     // A batch is cut into `groups` picture groups whose kernel sequences run on separate streams, forked from and
     // joined back into `st`: the latency-bound wavefront kernels of one group overlap the issue-bound kernels
@@ -110,6 +195,7 @@ struct H264B2Context {
     cudaStream_t st_g[MAX_GROUPS], st_side[MAX_GROUPS];
     cudaEvent_t fork_ev, join_ev[MAX_GROUPS], side_fork[MAX_GROUPS], side_join[MAX_GROUPS];
     // descriptor ring
+    PullDesc *h_pull, *h_pull_dev; int h2d_ctas;     // H264B2_H2D_ZEROCOPY: per-slot lists of host spans for k_pull
     PicDev *h_desc, *h_desc_dev, *d_desc;     // h_desc: mapped pinned host memory, h_desc_dev: its device alias
     cudaEvent_t desc_ev[DESC_RING];
     int desc_next;
@@ -118,9 +204,9 @@ struct H264B2Context {
     cudaEvent_t h2d_done[NSLOT], h2d_done2[NSLOT], compute_done[NSLOT];
     int slot_next;
     // read-back staging
-    uint8_t *out_stage[2]; size_t out_cap[2]; cudaEvent_t out_ready[2], out_done[2]; int out_next;
+    uint8_t *out_stage[NOUT]; size_t out_cap[NOUT]; cudaEvent_t out_ready[NOUT], out_done[NOUT]; int out_next;
     uint8_t **d_ptrs; unsigned long long *d_sums; unsigned long long *h_sums; uint8_t **h_ptrs;
-    uint8_t **h_snap[2], **h_snap_dev[2];     // mapped pinned pointer lists for k_snapshot
+    uint8_t **h_snap[NOUT], **h_snap_dev[NOUT];     // mapped pinned pointer lists for k_snapshot
     uint8_t *bgr; size_t bgr_cap;             // BGR24 output staging
     size_t bs_stride;                         // words per stream in bs
     // timing
@@ -129,12 +215,12 @@ struct H264B2Context {
     cudaEvent_t *ev; int ev_used; int ev_class[EV_POOL / 2];
     float class_ms[KCLASSES]; long long class_launches[KCLASSES];
     // optional timeline trace (H264B2_TRACE=path): per host submit, events at H2D start/end and compute start/end
-    int trace; int trace_n; cudaEvent_t trace_ev[256][4]; const char *trace_path;
+    int trace; int trace_n; cudaEvent_t trace_ev[256][6]; const char *trace_path;
 };
 
-static void trace_mark(H264B2Context *c, int which, cudaStream_t s) {
-    if (!c->trace || c->trace_n >= 256) return;
-    cudaEvent_t &e = c->trace_ev[c->trace_n][which];
+static void trace_mark(H264B2Context *c, int which, cudaStream_t s, int back = 0) {
+    if (!c->trace || c->trace_n - back >= 256 || c->trace_n - back < 0) return;
+    cudaEvent_t &e = c->trace_ev[c->trace_n - back][which];
     if (!e) cudaEventCreate(&e);
     cudaEventRecord(e, s);
 }
@@ -142,11 +228,11 @@ static void trace_dump(H264B2Context *c) {
     if (!c->trace || c->trace_n < 2) return;
     FILE *f = fopen(c->trace_path, "a");
     if (!f) return;
-    fprintf(f, "# batch h2d_start h2d_end compute_start compute_end (ms since first H2D start)\n");
+    fprintf(f, "# batch h2d_start h2d_end compute_start compute_end d2h_start d2h_end (ms since first H2D start)\n");
     for (int i = 0; i < c->trace_n; i++) {
-        float t[4];
-        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], c->trace_ev[0][0], c->trace_ev[i][k]);
-        fprintf(f, "%d %.3f %.3f %.3f %.3f\n", i, t[0], t[1], t[2], t[3]);
+        float t[6] = {0, 0, 0, 0, -1, -1};
+        for (int k = 0; k < 6; k++) if (c->trace_ev[i][k]) { if (cudaEventElapsedTime(&t[k], c->trace_ev[0][0], c->trace_ev[i][k]) != cudaSuccess) { cudaGetLastError(); t[k] = -1; } }
+        fprintf(f, "%d %.3f %.3f %.3f %.3f %.3f %.3f\n", i, t[0], t[1], t[2], t[3], t[4], t[5]);
     }
     fclose(f);
     c->trace_n = 0;
@@ -239,11 +325,13 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     }
     CK(cudaMalloc(&c->progress, c->progress_ints * 4));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+    { const char *e = getenv("H264B2_H2D_ZEROCOPY"); int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&c->st_h2d, cudaStreamNonBlocking, (e && atoi(e) > 0) ? hi : lo)); }
     CK(cudaStreamCreateWithFlags(&c->st_h2d2, cudaStreamNonBlocking));
     { const char *e = getenv("H264B2_H2D_STREAMS"); c->h2d_streams = (e && atoi(e) == 2) ? 2 : 1; }      // measured on the B200 box: 2 queues 10.8k frames/s e2e, 1 queue 11.1k
-    { const char *e = getenv("H264B2_D2H_CHUNK_MB"); c->d2h_chunk = (size_t)(e && atoi(e) > 0 ? atoi(e) : 1) << 20; }      // default: one transfer per picture (64 MB merged transfers measured 6 % slower with H2D running)
-    CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+    { const char *e = getenv("H264B2_D2H_CHUNK_MB"); c->d2h_chunk = e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : 0; }      // 0 = adaptive, see h264b2_read_pictures_async
+    { const char *e = getenv("H264B2_D2H_ZEROCOPY"); c->d2h_ctas = e ? atoi(e) : 0; c->d2h_zerocopy = c->d2h_ctas > 0; }
+    { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&c->st_d2h, cudaStreamNonBlocking, c->d2h_zerocopy ? hi : lo)); }
     for (int i = 0; i < MAX_GROUPS; i++) {
         CK(cudaStreamCreateWithFlags(&c->st_g[i], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
@@ -252,14 +340,17 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     CK(cudaHostAlloc(&c->h_desc, sizeof(PicDev) * n_streams * DESC_RING, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void **)&c->h_desc_dev, c->h_desc, 0));
-    for (int i = 0; i < 2; i++) {
-        CK(cudaHostAlloc(&c->h_snap[i], sizeof(uint8_t *) * n_streams, cudaHostAllocMapped));
+    { const char *e = getenv("H264B2_H2D_ZEROCOPY"); c->h2d_ctas = e ? atoi(e) : 0; }
+    CK(cudaHostAlloc(&c->h_pull, sizeof(PullDesc) * n_streams * 8 * NSLOT, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&c->h_pull_dev, c->h_pull, 0));
+    for (int i = 0; i < NOUT; i++) {
+        CK(cudaHostAlloc(&c->h_snap[i], sizeof(uint8_t *) * n_streams * 2, cudaHostAllocMapped));      // [0, n): surfaces, [n, 2n): host destinations
         CK(cudaHostGetDevicePointer((void **)&c->h_snap_dev[i], c->h_snap[i], 0));
     }
     CK(cudaMalloc(&c->d_desc, sizeof(PicDev) * n_streams * DESC_RING));
     for (int i = 0; i < DESC_RING; i++) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < NSLOT; i++) { CK(cudaEventCreateWithFlags(&c->h2d_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->h2d_done2[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming)); }
-    for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->out_ready[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming)); }
+    for (int i = 0; i < NOUT; i++) { CK(cudaEventCreateWithFlags(&c->out_ready[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming)); }
     CK(cudaMalloc(&c->d_ptrs, sizeof(uint8_t *) * n_streams));
     CK(cudaMalloc(&c->d_sums, 8 * n_streams));
     CK(cudaMallocHost(&c->h_sums, 8 * n_streams));
@@ -278,9 +369,9 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->bgr) cudaFree(c->bgr);
-    cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_snap[0]); cudaFreeHost(c->h_snap[1]);
+    cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_pull); for (int i = 0; i < NOUT; i++) cudaFreeHost(c->h_snap[i]);
     for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->h2d_done2[i]); cudaEventDestroy(c->compute_done[i]); }
-    for (int i = 0; i < 2; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
+    for (int i = 0; i < NOUT; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
     for (int i = 0; i < DESC_RING; i++) cudaEventDestroy(c->desc_ev[i]);
     cudaFree(c->d_ptrs); cudaFree(c->d_sums); cudaFreeHost(c->h_sums); cudaFreeHost(c->h_ptrs);
     for (int i = 0; i < EV_POOL; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -321,17 +412,18 @@ static int validate(const H264B2Context *c, int n_pics, const int32_t *sids, con
         if (!p.mb_info || !p.intra_modes || !p.coef_offset || !p.weights || p.n_weights < 1) return fail(-3, "submit: missing array");
         if (p.has_inter && !p.motion) return fail(-3, "submit: has_inter without motion");
         if (p.n_coefs && !p.coefs) return fail(-3, "submit: n_coefs without coefs");
+        if (p.packed & ~(H264B2_PACKED_COEFS | H264B2_PACKED_MOTION)) return fail(-3, "submit: unknown bits in packed (%d)", p.packed);
         if (p.custom_scaling && (!p.level_scale4 || !p.level_scale8)) return fail(-3, "submit: custom_scaling without tables");
     }
     return 0;
 }
 
 // enqueue the kernels of one batch; every array pointer in pics[] is a device pointer
-static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264B2PicParams *pics) {
+static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264B2PicParams *pics, const uint32_t *const *packed = nullptr, const uint32_t *const *packed_motion = nullptr) {
     const int ring = c->desc_next; c->desc_next = (c->desc_next + 1) % DESC_RING;
     CK(cudaEventSynchronize(c->desc_ev[ring]));
     PicDev *hd = c->h_desc + (size_t)ring * c->n_streams, *dd = c->d_desc + (size_t)ring * c->n_streams;
-    int any_inter = 0, any_deblock = 0;
+    int any_inter = 0, any_deblock = 0, any_packed = 0, any_packed_motion = 0;
     // descriptors are laid out progressive pictures first, then "generic" ones (MBAFF, or wider than the fast paths
     // support): the wavefront kernels are launched once per kind, each with only its own code path compiled in
     std::vector<int> order; order.reserve(n);
@@ -343,7 +435,8 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         const H264B2PicParams &p = pics[i];
         PicDev &d = hd[j];
         d.info = p.mb_info; d.modes = p.intra_modes; d.coef_off = p.coef_offset; d.motion = p.has_inter ? p.motion : nullptr;
-        d.weights = p.weights; d.coefs = p.coefs;
+        d.weights = p.weights; d.coefs = p.coefs; d.packed = packed ? packed[i] : nullptr; d.packed_motion = packed_motion ? packed_motion[i] : nullptr;
+        any_packed |= d.packed != nullptr || d.packed_motion != nullptr; any_packed_motion |= d.packed_motion != nullptr;
         d.ls4 = p.custom_scaling ? p.level_scale4 : c->ls_flat;
         d.ls8 = p.custom_scaling ? p.level_scale8 : c->ls_flat + 2 * 2 * 6 * 16;
         d.stream_base = c->surfaces + (size_t)sids[i] * c->spp * c->frame_bytes;
@@ -364,6 +457,8 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
     k_prologue<<<1, 256, 0, c->st>>>((const uint4 *)(c->h_desc_dev + (size_t)ring * c->n_streams), (uint4 *)dd, (int)(sizeof(PicDev) * n / 16), c->progress, (int)c->progress_ints);
     CK(cudaEventRecord(c->desc_ev[ring], c->st));
     for (int j = 0; j < n; j++) if (pics[order[j]].clear_surface) CK(cudaMemsetAsync(hd[j].dst, 0, c->frame_bytes, c->st));
+    if (any_packed) k_expand<<<dim3(32, n, any_packed_motion ? 2 : 1), 256, 0, c->st>>>(dd);
+    if (any_packed_motion) k_unmotion<<<dim3((c->nmb * 2 + 255) / 256, n), 256, 0, c->st>>>(dd);
     class_end(c, 0, c->st);
     int G = c->groups;
     while (G > 1 && n / G < c->group_min) G--;
@@ -430,8 +525,74 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
 extern "C" int h264b2_submit_device(H264B2Context *c, int n_pics, const int32_t *sids, const H264B2PicParams *pics) {
     int r = validate(c, n_pics, sids, pics);
     if (r) return r;
+    for (int i = 0; i < n_pics; i++) if (pics[i].packed) return fail(-3, "submit_device: packed arrays travel through h264b2_submit (host arrays)");
     CK(cudaSetDevice(c->device));
     return launch_batch(c, n_pics, sids, pics);
+}
+
+// ---- packed coefficient transport, host side (layout: see k_expand)
+extern "C" size_t h264b2_pack_coefs_bound(uint32_t n_coefs) {
+    const size_t nc = ((size_t)n_coefs + 15) / 16, ng = (nc + 31) / 32;
+    return (16 + ng * 4 + ((nc + 1) & ~(size_t)1) * 2 + nc * 32 + 15) & ~(size_t)15;
+}
+extern "C" int h264b2_pack_coefs(const int16_t *dense, uint32_t n_coefs, void *out, size_t cap, size_t *bytes) {
+    if ((!dense && n_coefs) || !out || !bytes || ((uintptr_t)out & 3)) return fail(-1, "pack_coefs: bad argument");
+    const size_t nc = ((size_t)n_coefs + 15) / 16, ng = (nc + 31) / 32;
+    const size_t fixed = 16 + ng * 4 + ((nc + 1) & ~(size_t)1) * 2;
+    if (cap < fixed) return fail(-3, "pack_coefs: output buffer too small");
+    uint32_t *hdr = (uint32_t *)out, *base = hdr + 4;
+    uint16_t *map = (uint16_t *)(base + ng);
+    int16_t *val = (int16_t *)((uint8_t *)out + fixed);
+    const size_t vcap = (cap - fixed) / 2;
+    size_t nv = 0;
+    if (nc & 1) map[nc] = 0;
+    for (size_t ch = 0; ch < nc; ch++) {
+        if ((ch & 31) == 0) base[ch >> 5] = (uint32_t)nv;
+        const size_t lo = ch * 16, hi = std::min<size_t>(lo + 16, n_coefs);
+        if (nv + 16 > vcap) {          // exact check only when space is short
+            size_t cnt = 0; for (size_t k = lo; k < hi; k++) cnt += dense[k] != 0;
+            if (nv + cnt > vcap) return fail(-3, "pack_coefs: output buffer too small");
+        }
+        uint32_t bm = 0;
+        if (hi - lo == 16) {               // most chunks hold nothing: test 32 bytes at once
+            uint64_t q[4]; memcpy(q, dense + lo, 32);
+            if (!(q[0] | q[1] | q[2] | q[3])) { map[ch] = 0; continue; }
+        }
+        for (size_t k = lo; k < hi; k++) { const int16_t v = dense[k]; val[nv] = v; const unsigned nz = v != 0; bm |= nz << (k - lo); nv += nz; }
+        map[ch] = (uint16_t)bm;
+    }
+    size_t total = fixed + nv * 2;
+    while (total & 15) { if (total + 2 <= cap) *(int16_t *)((uint8_t *)out + total) = 0; total += 2; }
+    if (total > cap) return fail(-3, "pack_coefs: output buffer too small");
+    hdr[0] = H264B2_PACK_MAGIC; hdr[1] = (uint32_t)nc; hdr[2] = (uint32_t)nv; hdr[3] = (uint32_t)total;
+    *bytes = total;
+    return 0;
+}
+extern "C" int h264b2_unpack_coefs(const void *packed, int16_t *dense, uint32_t n_coefs) {
+    const uint32_t *hdr = (const uint32_t *)packed;
+    if (!packed || (!dense && n_coefs) || hdr[0] != H264B2_PACK_MAGIC || hdr[1] != (n_coefs + 15) / 16) return fail(-3, "unpack_coefs: malformed blob");
+    const size_t nc = hdr[1], ng = (nc + 31) / 32;
+    const uint16_t *map = (const uint16_t *)(hdr + 4 + ng);
+    const int16_t *val = (const int16_t *)(map + ((nc + 1) & ~(size_t)1));
+    size_t nv = 0;
+    for (size_t k = 0; k < n_coefs; k++) dense[k] = ((map[k >> 4] >> (k & 15)) & 1) ? val[nv++] : (int16_t)0;
+    return nv == hdr[2] ? 0 : fail(-3, "unpack_coefs: value count mismatch");
+}
+
+extern "C" int h264b2_pack_motion(const H264B2MbMotion *motion, uint32_t n_mbs, void *out, size_t cap, size_t *bytes) {
+    if ((!motion && n_mbs) || !out || !bytes) return fail(-1, "pack_motion: bad argument");
+    std::vector<uint32_t> tmp((size_t)n_mbs * (sizeof(H264B2MbMotion) / 4));
+    if (n_mbs) memcpy(tmp.data(), motion, (size_t)n_mbs * sizeof(H264B2MbMotion));
+    for (size_t a = 0; a < n_mbs; a++)
+        for (int l = 0; l < 2; l++) { uint32_t *w = tmp.data() + a * (sizeof(H264B2MbMotion) / 4) + l * 16; for (int r = 15; r >= 1; r--) w[r] ^= w[r - 1]; }
+    return h264b2_pack_coefs((const int16_t *)tmp.data(), (uint32_t)(n_mbs * (sizeof(H264B2MbMotion) / 2)), out, cap, bytes);
+}
+extern "C" int h264b2_unpack_motion(const void *packed, H264B2MbMotion *motion, uint32_t n_mbs) {
+    int r = h264b2_unpack_coefs(packed, (int16_t *)motion, (uint32_t)(n_mbs * (sizeof(H264B2MbMotion) / 2)));
+    if (r) return r;
+    for (size_t a = 0; a < n_mbs; a++)
+        for (int l = 0; l < 2; l++) { uint32_t *w = (uint32_t *)&motion[a].mv[l][0][0]; for (int i = 1; i < 16; i++) w[i] ^= w[i - 1]; }
+    return 0;
 }
 
 // ---- host-array submit: one DMA per contiguous span, straight from the caller's memory (pinned memory
@@ -444,20 +605,41 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
     if (r) return r;
     CK(cudaSetDevice(c->device));
     const int slot = c->slot_next; c->slot_next = (c->slot_next + 1) % NSLOT;
+    CK(cudaEventSynchronize(c->h2d_done[slot]));      // the host arrays of the submit NSLOT calls ago have left (API contract)
+    if (c->h2d_streams > 1) CK(cudaEventSynchronize(c->h2d_done2[slot]));
     std::vector<H264B2PicParams> dev(pics, pics + n_pics);
     // plan
     size_t need = 0;
     std::vector<Span> spans; spans.reserve((size_t)n_pics * 8);
+    std::vector<const uint32_t *> packed((size_t)n_pics, nullptr), packed_m((size_t)n_pics, nullptr);
+    bool any_packed = false, any_packed_m = false;
     for (int i = 0; i < n_pics; i++) {
         H264B2PicParams &p = dev[i];
         const size_t nmb = (size_t)c->nmb;
+        size_t coef_bytes = (size_t)p.n_coefs * 2;
+        size_t motion_bytes = p.has_inter ? nmb * sizeof(H264B2MbMotion) : 0;
+        if ((p.packed & H264B2_PACKED_MOTION) && p.has_inter) {
+            const uint32_t *hdr = (const uint32_t *)p.motion;
+            const uint32_t want = (uint32_t)((nmb * (sizeof(H264B2MbMotion) / 2) + 15) / 16);
+            if (((uintptr_t)hdr & 15) || hdr[0] != H264B2_PACK_MAGIC || hdr[1] != want || hdr[3] < 16 || (hdr[3] & 15)) return fail(-3, "submit: malformed packed motion blob (picture %d)", i);
+            motion_bytes = hdr[3];
+            need += al256((size_t)want * 32) + 256;
+            any_packed_m = true;
+        }
+        if ((p.packed & H264B2_PACKED_COEFS) && p.n_coefs) {
+            const uint32_t *hdr = (const uint32_t *)p.coefs;
+            if (((uintptr_t)hdr & 15) || hdr[0] != H264B2_PACK_MAGIC || hdr[1] != (p.n_coefs + 15) / 16 || hdr[3] < 16 || (hdr[3] & 15)) return fail(-3, "submit: malformed packed coefficient blob (picture %d)", i);
+            coef_bytes = hdr[3];
+            need += al256((size_t)hdr[1] * 32) + 256;      // the dense array k_expand rebuilds
+            any_packed = true;
+        }
         Span s[8] = {
             { (const uint8_t *)p.mb_info, nmb * sizeof(H264B2MbInfo), (const void **)&p.mb_info },
             { (const uint8_t *)p.intra_modes, nmb * 8, (const void **)&p.intra_modes },
             { (const uint8_t *)p.coef_offset, nmb * 4, (const void **)&p.coef_offset },
-            { (const uint8_t *)(p.has_inter ? p.motion : nullptr), p.has_inter ? nmb * sizeof(H264B2MbMotion) : 0, (const void **)&p.motion },
+            { (const uint8_t *)(p.has_inter ? p.motion : nullptr), motion_bytes, (const void **)&p.motion },
             { (const uint8_t *)p.weights, (size_t)p.n_weights * sizeof(H264B2Weight), (const void **)&p.weights },
-            { (const uint8_t *)p.coefs, (size_t)p.n_coefs * 2, (const void **)&p.coefs },
+            { (const uint8_t *)p.coefs, coef_bytes, (const void **)&p.coefs },
             { (const uint8_t *)(p.custom_scaling ? p.level_scale4 : nullptr), p.custom_scaling ? (size_t)2 * 2 * 6 * 16 * 2 : 0, (const void **)&p.level_scale4 },
             { (const uint8_t *)(p.custom_scaling ? p.level_scale8 : nullptr), p.custom_scaling ? (size_t)2 * 2 * 6 * 64 * 2 : 0, (const void **)&p.level_scale8 },
         };
@@ -476,6 +658,9 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
     size_t off = 0;
     size_t i = 0;
     unsigned ncopy = 0;
+    PullDesc *pull = c->h_pull + (size_t)slot * c->n_streams * 8;
+    int npull = 0;
+    bool zc = c->h2d_ctas > 0;
     while (i < spans.size()) {
         size_t j = i;
         const uint8_t *lo = spans[i].p; const uint8_t *hi = lo + spans[i].n;
@@ -483,17 +668,41 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
         // keep the host address's offset within 256 so that every array keeps its natural alignment
         off = al256(off) + ((size_t)(uintptr_t)lo & 255);
         // picture-sized DMAs leave gaps on one copy queue (profiles/r01_pcie_probe.txt): alternate between two
-        CK(cudaMemcpyAsync(c->arena[slot] + off, lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, (c->h2d_streams > 1 && (ncopy++ & 1)) ? c->st_h2d2 : c->st_h2d));
+        cudaPointerAttributes at;
+        if (zc && cudaPointerGetAttributes(&at, lo) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            pull[npull].src = (const uint8_t *)at.devicePointer; pull[npull].dst = c->arena[slot] + off; pull[npull].bytes = (size_t)(hi - lo); npull++;
+        } else {
+            if (zc) cudaGetLastError();
+            CK(cudaMemcpyAsync(c->arena[slot] + off, lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, (c->h2d_streams > 1 && (ncopy & 1)) ? c->st_h2d2 : c->st_h2d));
+        }
+        ncopy++;
         for (size_t k = i; k <= j; k++) *spans[k].slot = c->arena[slot] + off + (spans[k].p - lo);
         off += (size_t)(hi - lo);
         i = j + 1;
     }
+    if (any_packed || any_packed_m) for (int k = 0; k < n_pics; k++) {
+        H264B2PicParams &p = dev[k];
+        if ((p.packed & H264B2_PACKED_COEFS) && p.n_coefs) {
+            packed[k] = (const uint32_t *)p.coefs;                 // the blob's device copy
+            off = al256(off);
+            p.coefs = (const int16_t *)(c->arena[slot] + off);      // where k_expand writes the dense array
+            off += (size_t)((p.n_coefs + 15) / 16) * 32;
+        }
+        if ((p.packed & H264B2_PACKED_MOTION) && p.has_inter) {
+            packed_m[k] = (const uint32_t *)p.motion;
+            off = al256(off);
+            p.motion = (const H264B2MbMotion *)(c->arena[slot] + off);
+            off += (((size_t)c->nmb * (sizeof(H264B2MbMotion) / 2) + 15) / 16) * 32;
+        }
+    }
+    if (npull) { k_pull<<<c->h2d_ctas, 256, 0, c->st_h2d>>>(c->h_pull_dev + (size_t)slot * c->n_streams * 8, npull); CK(cudaGetLastError()); }
+    c->h2d_last_bytes = off; c->h2d_last_copies = ncopy;
     CK(cudaEventRecord(c->h2d_done[slot], c->st_h2d));
     trace_mark(c, 1, c->st_h2d);
     CK(cudaStreamWaitEvent(c->st, c->h2d_done[slot], 0));
     if (c->h2d_streams > 1) { CK(cudaEventRecord(c->h2d_done2[slot], c->st_h2d2)); CK(cudaStreamWaitEvent(c->st, c->h2d_done2[slot], 0)); }
     trace_mark(c, 2, c->st);
-    r = launch_batch(c, n_pics, sids, dev.data());
+    r = launch_batch(c, n_pics, sids, dev.data(), any_packed ? packed.data() : nullptr, any_packed_m ? packed_m.data() : nullptr);
     if (r) return r;
     CK(cudaEventRecord(c->compute_done[slot], c->st));
     trace_mark(c, 3, c->st);
@@ -539,7 +748,7 @@ extern "C" int h264b2_write_picture(H264B2Context *c, int sid, int surface, cons
 extern "C" int h264b2_read_pictures_async(H264B2Context *c, int n, const int32_t *sids, const int32_t *surfaces, uint8_t *const *host) {
     if (!c || n < 1 || n > c->n_streams || !sids || !surfaces || !host) return fail(-1, "read_pictures_async: bad argument");
     CK(cudaSetDevice(c->device));
-    const int s = c->out_next; c->out_next ^= 1;
+    const int s = c->out_next; c->out_next = (c->out_next + 1) % NOUT;
     const size_t need = (size_t)n * c->frame_bytes;
     if (c->out_cap[s] < need) {
         CK(cudaEventSynchronize(c->out_done[s]));
@@ -553,14 +762,35 @@ extern "C" int h264b2_read_pictures_async(H264B2Context *c, int n, const int32_t
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->out_ready[s], c->st));
     CK(cudaStreamWaitEvent(c->st_d2h, c->out_ready[s], 0));
+    trace_mark(c, 4, c->st_d2h, 1);
+    if (c->d2h_zerocopy) {
+        bool ok = true;
+        for (int i = 0; i < n && ok; i++) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, host[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { cudaGetLastError(); ok = false; break; }
+            c->h_snap[s][c->n_streams + i] = (uint8_t *)at.devicePointer;
+        }
+        if (ok) {
+            k_drain<<<c->d2h_ctas, 256, 0, c->st_d2h>>>(c->out_stage[s], c->h_snap_dev[s] + c->n_streams, c->frame_bytes / 16, n);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(c->out_done[s], c->st_d2h));
+            return 0;
+        }
+    }
     // the staging buffer is contiguous: destinations that are adjacent in host memory leave as ONE transfer (bounded chunks)
-    const int per = (int)std::max<size_t>(1, c->d2h_chunk / c->frame_bytes);
+    // Policy (profiles/r01_pcie_probe2.txt, B200 box): with picture-sized H2D transfers in flight a merged read-back starves
+    // them (e2e 11.1k -> 9.8k frames/s); when the submits arrive as batch-sized transfers, merging the read-back as well lifts
+    // both directions to ~50 GB/s.  So: merge iff the last submit averaged >= 16 MB per transfer (or H264B2_D2H_CHUNK_MB says so).
+    size_t chunk = c->d2h_chunk;
+    if (!chunk) chunk = (c->h2d_last_copies && c->h2d_last_bytes / c->h2d_last_copies >= ((size_t)16 << 20)) ? (size_t)1 << 30 : 1;
+    const int per = (int)std::max<size_t>(1, chunk / c->frame_bytes);
     for (int i = 0; i < n; ) {
         int j = i + 1;
         while (j < n && j - i < per && host[j] == host[j - 1] + c->frame_bytes) j++;
         CK(cudaMemcpyAsync(host[i], c->out_stage[s] + (size_t)i * c->frame_bytes, (size_t)(j - i) * c->frame_bytes, cudaMemcpyDeviceToHost, c->st_d2h));
         i = j;
     }
+    trace_mark(c, 5, c->st_d2h, 1);
     CK(cudaEventRecord(c->out_done[s], c->st_d2h));
     return 0;
 }
@@ -630,7 +860,7 @@ extern "C" int h264b2_timer_stop(H264B2Context *c, float *ms) {
     if (!c || !ms) return fail(-1, "bad argument");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->st_h2d)); CK(cudaStreamSynchronize(c->st_h2d2));
-    for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(c->st, c->out_done[i], 0));   // t1 also covers pending read-backs
+    for (int i = 0; i < NOUT; i++) CK(cudaStreamWaitEvent(c->st, c->out_done[i], 0));   // t1 also covers pending read-backs
     CK(cudaEventRecord(c->t1, c->st));
     CK(cudaEventSynchronize(c->t1));
     CK(cudaStreamSynchronize(c->st_d2h));

@@ -157,6 +157,7 @@ int CH264VideoDecoderB200::open_bitstream(const char *url) {
     pc.ctx = ctx;
     if (h264b2_host_alloc(ctx, (size_t)wmb * hmb * 384, (void **)&frame)) FAIL(-3, "open: %s", h264b2_last_error());
     if (h264b2_front_create(&fe, pin_alloc, pin_free, &pc) || h264b2_front_open_file(fe, url)) FAIL(-1, "open: %s", fe ? h264b2_front_last_error(fe) : "out of memory");
+    h264b2_front_set_packed(fe, getenv("H264B2_PLAIN_ARRAYS") ? 0 : (H264B2_PACKED_COEFS | H264B2_PACKED_MOTION));      // packed levels and motion over PCIe unless told otherwise
     producer = std::thread([&] {
         for (;;) {
             H264B2FrontEvent e;
@@ -176,7 +177,7 @@ int CH264VideoDecoderB200::open_bitstream(const char *url) {
                 if (!ev.block) { ret = -3; snprintf(m_error, sizeof m_error, "open: out of page-locked memory"); break; }
                 if (h264b2_submit(ctx, 1, &sid, &ev.params)) { ret = -3; snprintf(m_error, sizeof m_error, "open: %s", h264b2_last_error()); break; }
                 inflight.push_back(ev.block);
-                while (inflight.size() > 3) { h264b2_front_release(fe, inflight.front()); inflight.pop_front(); }
+                while (inflight.size() > H264B2_SUBMIT_DEPTH) { h264b2_front_release(fe, inflight.front()); inflight.pop_front(); }
                 surf_poc[ev.surface] = ev.hdr.poc; surf_idx[ev.surface] = ev.decode_idx; surf_type[ev.surface] = ev.hdr.slice_type; surf_mbaff[ev.surface] = ev.hdr.mbaff;
             } else if (ev.kind == H264B2_EV_OUTPUT) {
                 if (h264b2_read_picture(ctx, 0, ev.surface, frame)) { ret = -3; snprintf(m_error, sizeof m_error, "open: %s", h264b2_last_error()); break; }

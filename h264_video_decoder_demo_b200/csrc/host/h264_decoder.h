@@ -67,6 +67,7 @@ struct Block { uint8_t *p; size_t cap; };
 struct Front {
     // configuration
     h264b2_front_alloc_fn alloc = nullptr; h264b2_front_free_fn free_fn = nullptr; void *alloc_user = nullptr;
+    bool packed_coefs = false, packed_motion = false;      // h264b2_front_set_packed
     std::string error;
     // stream
     std::vector<uint8_t> file; const uint8_t *data = nullptr; size_t size = 0, nal_pos = 0;

@@ -443,8 +443,10 @@ void Front::emit_picture(int deblock_enable) {
     for (int l = 0; l < 6 && flat; l++) { for (int k = 0; k < 16; k++) if (h.ScalingList4x4[l][k] != 16) flat = false; for (int k = 0; k < 64; k++) if (h.ScalingList8x8[l][k] != 16) flat = false; }
     { uint32_t next = (uint32_t)coefs.size(); for (int a = nmb - 1; a >= 0; a--) { if (info[a].mb_class == H264B2_MB_NA) coff[a] = next; else next = coff[a]; } }
     while (coefs.size() % 4) coefs.push_back(0);
-    const size_t b_info = (size_t)nmb * sizeof(H264B2MbInfo), b_modes = (size_t)nmb * 8, b_coff = (size_t)nmb * 4, b_mot = has_inter ? (size_t)nmb * sizeof(H264B2MbMotion) : 0;
-    const size_t b_w = weights.size() * sizeof(H264B2Weight), b_c = coefs.size() * 2, b_ls = flat ? 0 : (size_t)(2 * 2 * 6 * 16 + 2 * 2 * 6 * 64) * 2;
+    const size_t b_info = (size_t)nmb * sizeof(H264B2MbInfo), b_modes = (size_t)nmb * 8, b_coff = (size_t)nmb * 4, b_mot = !has_inter ? 0 : packed_motion ? h264b2_pack_coefs_bound((uint32_t)nmb * (uint32_t)(sizeof(H264B2MbMotion) / 2)) : (size_t)nmb * sizeof(H264B2MbMotion);
+    const bool pack = packed_coefs && !coefs.empty();
+    size_t pack_slack = 0;
+    const size_t b_w = weights.size() * sizeof(H264B2Weight), b_c = pack ? h264b2_pack_coefs_bound((uint32_t)coefs.size()) : coefs.size() * 2, b_ls = flat ? 0 : (size_t)(2 * 2 * 6 * 16 + 2 * 2 * 6 * 64) * 2;
     // every array starts on a 64-byte boundary inside the block: the engine keeps host alignment on the device and its kernels
     // read records with 16-byte loads
     auto al = [](size_t n) { return (n + 63) & ~(size_t)63; };
@@ -467,9 +469,19 @@ void Front::emit_picture(int deblock_enable) {
         memcpy(q, info.data(), b_info); p.mb_info = (const H264B2MbInfo *)q; q += al(b_info);
         memcpy(q, modes.data(), b_modes); p.intra_modes = (const uint64_t *)q; q += al(b_modes);
         memcpy(q, coff.data(), b_coff); p.coef_offset = (const uint32_t *)q; q += al(b_coff);
-        if (has_inter) { memcpy(q, s.motion.data(), b_mot); p.motion = (const H264B2MbMotion *)q; q += al(b_mot); }
+        if (has_inter && packed_motion) {
+            size_t used = 0;
+            if (h264b2_pack_motion(s.motion.data(), (uint32_t)nmb, q, b_mot, &used)) error = "motion packing failed";
+            p.packed |= H264B2_PACKED_MOTION; pack_slack += al(b_mot) - al(used);
+            p.motion = (const H264B2MbMotion *)q; q += al(b_mot);
+        } else if (has_inter) { memcpy(q, s.motion.data(), b_mot); p.motion = (const H264B2MbMotion *)q; q += al(b_mot); }
         memcpy(q, weights.data(), b_w); p.weights = (const H264B2Weight *)q; q += al(b_w);
-        if (b_c) memcpy(q, coefs.data(), b_c);
+        if (pack) {
+            size_t used = 0;
+            if (h264b2_pack_coefs(coefs.data(), (uint32_t)coefs.size(), q, b_c, &used)) error = "coefficient packing failed";
+            p.packed |= H264B2_PACKED_COEFS;
+            pack_slack += al(b_c) - al(used);
+        } else if (b_c) memcpy(q, coefs.data(), b_c);
         p.coefs = (const int16_t *)q; q += al(b_c);
         if (!flat) {
             // LevelScale in LIST order (PB:4852-4989 per scan position; chroma uses the luma list, Q7): [intra/inter][frame/field scan][qP%6][k]
@@ -490,7 +502,7 @@ void Front::emit_picture(int deblock_enable) {
             p.level_scale4 = (const int16_t *)q; p.level_scale8 = (const int16_t *)q + 2 * 2 * 6 * 16;
         }
     }
-    e.block = blk; e.block_bytes = total;
+    e.block = blk; e.block_bytes = total - pack_slack;      // bytes that travel
     // what later pictures read from this one (co-located macroblocks)
     for (int a = 0; a < nmb; a++) {
         const MbT &m = mbs[a]; ColMb &c = s.col[a];
@@ -521,6 +533,7 @@ extern "C" int h264b2_front_create(H264B2Front **f, h264b2_front_alloc_fn alloc,
     return 0;
 }
 extern "C" int h264b2_front_destroy(H264B2Front *f) { delete f; return 0; }
+extern "C" int h264b2_front_set_packed(H264B2Front *f, int flags) { if (!f) return -1; f->f.packed_coefs = (flags & H264B2_PACKED_COEFS) != 0; f->f.packed_motion = (flags & H264B2_PACKED_MOTION) != 0; return 0; }
 extern "C" int h264b2_front_open_memory(H264B2Front *f, const uint8_t *data, size_t bytes) {
     if (!f || !data) return -1;
     f->f.data = data; f->f.size = bytes; f->f.nal_pos = 0;

@@ -1,4 +1,5 @@
 // h264_multi.cpp — see include/h264_multi_b200.h.  Parser thread pool -> per-stream event queues -> one submit thread.
+#include <stdlib.h>
 #include "h264_multi_b200.h"
 #include "h264_front_b200.h"
 #include "h264_recon_b200.h"
@@ -86,6 +87,7 @@ extern "C" int h264b2_multi_decode(int device, int n_inputs, const char *const *
     for (int s = 0; s < n_streams; s++) {
         const std::vector<uint8_t> &v = bufs[buf_of[st[s].owner]];
         if (h264b2_front_create(&st[s].fe, pin_alloc, pin_free, &pin) || h264b2_front_open_range(st[s].fe, v.data(), v.size(), st[s].begin, st[s].end, st[s].more_follows)) { first_error = st[s].fe ? h264b2_front_last_error(st[s].fe) : "out of memory"; break; }
+        h264b2_front_set_packed(st[s].fe, getenv("H264B2_PLAIN_ARRAYS") ? 0 : (H264B2_PACKED_COEFS | H264B2_PACKED_MOTION));      // packed levels and motion over PCIe unless told otherwise
     }
     H264B2MultiStats S; memset(&S, 0, sizeof S);
     S.threads = n_threads; S.streams = n_inputs; S.units = n_streams; S.width_mbs = wmb; S.height_mbs = hmb;
@@ -120,7 +122,7 @@ extern "C" int h264b2_multi_decode(int device, int n_inputs, const char *const *
                 }
             });
         // ---- submit thread (this one)
-        std::deque<std::vector<std::pair<int, void *>>> inflight;       // blocks of the last submits (DMA may be pending for 3 of them)
+        std::deque<std::vector<std::pair<int, void *>>> inflight;       // blocks of the last submits (DMA may be pending for H264B2_SUBMIT_DEPTH of them)
         int active = n_streams, rounds_since_sync = 0;
         std::vector<int32_t> sids, surfs; std::vector<uint8_t *> hptr; std::vector<H264B2PicParams> pics; std::vector<uint64_t> sums;
         while (active > 0 && rc == 0) {
@@ -171,7 +173,7 @@ extern "C" int h264b2_multi_decode(int device, int n_inputs, const char *const *
                 if (h264b2_submit(ctx, (int)pics.size(), sids.data(), pics.data())) { rc = -3; first_error = h264b2_last_error(); break; }
                 S.pictures += (int64_t)pics.size(); S.submits++;
                 inflight.push_back(blocks);
-                while (inflight.size() > 3) { for (auto &b : inflight.front()) h264b2_front_release(st[b.first].fe, b.second); inflight.pop_front(); }
+                while (inflight.size() > H264B2_SUBMIT_DEPTH) { for (auto &b : inflight.front()) h264b2_front_release(st[b.first].fe, b.second); inflight.pop_front(); }
             }
         }
         { std::lock_guard<std::mutex> l(mu); cancel = true; cv_space.notify_all(); }

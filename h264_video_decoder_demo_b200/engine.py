@@ -39,6 +39,11 @@ _PROTOS = {
     "h264b2_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "h264b2_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "h264b2_sync": (C.c_int, [C.c_void_p]),
+    "h264b2_pack_coefs_bound": (C.c_size_t, [C.c_uint32]),
+    "h264b2_pack_coefs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "h264b2_unpack_coefs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "h264b2_pack_motion": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "h264b2_unpack_motion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "h264b2_timer_start": (C.c_int, [C.c_void_p]),
     "h264b2_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "h264b2_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
@@ -65,6 +70,56 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         _LIB = lib
     return _LIB
+
+
+def pack_coefs(dense: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Packed coefficient blob (h264b2_pack_coefs) of a dense int16 level array; a host function, no GPU needed.
+    `out`: optional uint8 buffer (16-byte aligned, e.g. page-locked) to pack into; returns the blob as a view of it."""
+    lib = load_library()
+    dense = np.ascontiguousarray(dense, dtype=np.int16)
+    bound = lib.h264b2_pack_coefs_bound(dense.size)
+    if out is None:
+        raw = np.empty(bound + 16, np.uint8)
+        o = (-raw.ctypes.data) % 16
+        out = raw[o:o + bound]
+    n = C.c_size_t()
+    rc = lib.h264b2_pack_coefs(dense.ctypes.data if dense.size else None, dense.size, out.ctypes.data, out.size, C.byref(n))
+    if rc != 0:
+        raise EngineError(f"h264b2_pack_coefs: {lib.h264b2_last_error().decode(errors='replace')}")
+    return out[:n.value]
+
+
+def pack_motion(motion: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Packed blob (h264b2_pack_motion) of a picture's H264B2MbMotion records (abi.MB_MOTION_DT)."""
+    lib = load_library()
+    motion = np.ascontiguousarray(motion)
+    n = motion.size
+    bound = lib.h264b2_pack_coefs_bound(n * 76)
+    if out is None:
+        raw = np.empty(bound + 16, np.uint8)
+        o = (-raw.ctypes.data) % 16
+        out = raw[o:o + bound]
+    nb = C.c_size_t()
+    if lib.h264b2_pack_motion(motion.ctypes.data if n else None, n, out.ctypes.data, out.size, C.byref(nb)) != 0:
+        raise EngineError(f"h264b2_pack_motion: {lib.h264b2_last_error().decode(errors='replace')}")
+    return out[:nb.value]
+
+
+def unpack_motion(blob: np.ndarray, n_mbs: int) -> np.ndarray:
+    from .abi import MB_MOTION_DT
+    lib = load_library()
+    m = np.zeros(n_mbs, MB_MOTION_DT)
+    if lib.h264b2_unpack_motion(blob.ctypes.data, m.ctypes.data if n_mbs else None, n_mbs) != 0:
+        raise EngineError(f"h264b2_unpack_motion: {lib.h264b2_last_error().decode(errors='replace')}")
+    return m
+
+
+def unpack_coefs(blob: np.ndarray, n_coefs: int) -> np.ndarray:
+    lib = load_library()
+    dense = np.empty(n_coefs, np.int16)
+    if lib.h264b2_unpack_coefs(blob.ctypes.data, dense.ctypes.data if n_coefs else None, n_coefs) != 0:
+        raise EngineError(f"h264b2_unpack_coefs: {lib.h264b2_last_error().decode(errors='replace')}")
+    return dense
 
 
 class Engine:

@@ -128,9 +128,11 @@ def parse_replay(buf, path: str = "<buffer>", max_pictures: Optional[int] = None
     return rp
 
 
-def pic_params(rp: Replay, pic: Picture, ptrs=None) -> PicParams:
+def pic_params(rp: Replay, pic: Picture, ptrs=None, packed_blob=None, packed_motion=None) -> PicParams:
     """Fill a PicParams for `pic`.  `ptrs` maps array name -> integer address (host or device);
-    when None the numpy arrays' own host addresses are used (keep `pic` alive while in use)."""
+    when None the numpy arrays' own host addresses are used (keep `pic` alive while in use).
+    `packed_blob`: uint8 array from engine.pack_coefs(pic.coefs) -> the picture travels with packed coefficients;
+    `packed_motion`: uint8 array from engine.pack_motion(pic.motion) -> ... with packed motion records (h264b2_submit only)."""
     p = PicParams()
     p.width_mbs, p.height_mbs, p.mbaff_frame_flag = rp.width_mbs, rp.height_mbs, pic.mbaff
     p.chroma_qp_offset[0], p.chroma_qp_offset[1] = pic.cqp
@@ -147,6 +149,10 @@ def pic_params(rp: Replay, pic: Picture, ptrs=None) -> PicParams:
 
     for name in ("mb_info", "intra_modes", "coef_offset", "motion", "weights", "coefs", "level_scale4", "level_scale8"):
         setattr(p, name, addr(name))
+    if packed_blob is not None and len(pic.coefs):
+        p.packed, p.coefs = p.packed | 1, packed_blob.ctypes.data
+    if packed_motion is not None and pic.has_inter and pic.motion is not None:
+        p.packed, p.motion = p.packed | 2, packed_motion.ctypes.data
     return p
 
 

@@ -52,6 +52,10 @@ typedef void (*h264b2_front_free_fn)(void *user, void *p);
 
 int h264b2_front_create(H264B2Front **f, h264b2_front_alloc_fn alloc, h264b2_front_free_fn free_fn, void *user);
 int h264b2_front_destroy(H264B2Front *f);
+/* flags = H264B2_PACKED_COEFS | H264B2_PACKED_MOTION: pictures leave with packed coefficients / motion records (params.packed,
+ * see h264b2_pack_coefs / h264b2_pack_motion): the form h264b2_submit wants for PCIe; default 0 = plain arrays (what the
+ * reference parser's containers hold). */
+int h264b2_front_set_packed(H264B2Front *f, int flags);
 /* Annex-B byte stream, whole file (the reference also reads whole NAL units from a file buffer). The memory must stay valid. */
 int h264b2_front_open_memory(H264B2Front *f, const uint8_t *data, size_t bytes);
 int h264b2_front_open_file(H264B2Front *f, const char *path);

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define H264B2_ABI_VERSION 1
+#define H264B2_ABI_VERSION 2
 
 /* ---- macroblock classes (derived from CH264MacroBlock::m_mb_pred_mode /
  *      m_name_of_mb_type, H264MacroBlock.h:210-211) ---- */
@@ -117,7 +117,9 @@ typedef struct H264B2PicParams {
     int32_t  n_weights;            /* entries in weights[] (>= 1) */
     uint32_t n_coefs;              /* int16 elements in coefs[] */
     int32_t  custom_scaling;       /* 0: Flat_4x4_16 / Flat_8x8_16; 1: level_scale4/8 given */
-    int32_t  reserved;
+    int32_t  packed;               /* h264b2_submit only, bit mask.  H264B2_PACKED_COEFS: coefs points at a blob written by
+                                      h264b2_pack_coefs() for the n_coefs levels; H264B2_PACKED_MOTION: motion points at a blob
+                                      written by h264b2_pack_motion() for the n_mbs records.  0: plain arrays */
     /* host (or device, see h264b2_submit_device) arrays.  Alignment: the engine keeps each array's address modulo 256 when it
      * copies it to the device and its kernels use 16-byte loads, so mb_info / motion / weights / coefs must start on 16-byte
      * boundaries (intra_modes 8, coef_offset 4); h264b2_host_alloc and the front end's picture blocks guarantee it. */
@@ -145,11 +147,33 @@ int h264b2_destroy(H264B2Context *ctx);
 /* Reconstruct one picture per listed stream (pictures of one stream are serial;
  * pictures of different streams run concurrently in one launch sequence).
  * Host arrays are DMA'd to the device asynchronously on a copy stream (one transfer per contiguous
- * span; pictures whose arrays lie back to back need one transfer) into a 3-deep device arena, so the
+ * span; pictures whose arrays lie back to back need one transfer) into an H264B2_SUBMIT_DEPTH-deep device arena, so the
  * copy of batch k+1 overlaps the kernels of batch k.  The call returns after enqueueing; the host
- * arrays must stay valid until h264b2_sync() or until 3 further submits have been issued.  stream_ids[i] in [0, n_streams). */
+ * arrays must stay valid until h264b2_sync() or until H264B2_SUBMIT_DEPTH further submits have RETURNED (a submit waits
+ * for the transfer issued H264B2_SUBMIT_DEPTH submits earlier before it reuses that arena slot).  stream_ids[i] in [0, n_streams). */
+#define H264B2_SUBMIT_DEPTH 4
 int h264b2_submit(H264B2Context *ctx, int n_pics, const int32_t *stream_ids,
                   const H264B2PicParams *pics);
+
+/* Packed coefficient transport ("sparse coefficient packing to cut PCIe traffic").  The levels the
+ * reference keeps in CH264MacroBlock::LumaLevel4x4 / LumaLevel8x8 / ChromaACLevel ... (H264MacroBlock.h:205-216) are almost all
+ * zero after entropy decoding (5.7 % non-zero in the bundled 1080p streams), so instead of the dense coefs[] the host may send
+ * one 16-bit significance map per chunk of 16 levels plus the non-zero levels (1.96 MB -> 0.25 MB per picture); the engine
+ * rebuilds the dense array in HBM (k_expand) before the residual kernel runs.  coef_offset[] / n_coefs / coef_mask keep their
+ * dense meaning.  h264b2_pack_coefs writes the blob (out: 16-byte aligned, cap >= h264b2_pack_coefs_bound(n_coefs) always
+ * suffices; *bytes = blob size, a multiple of 16); set packed |= H264B2_PACKED_COEFS and coefs = blob.  The pack/unpack
+ * functions are plain host functions (no GPU needed). */
+#define H264B2_PACKED_COEFS  1
+#define H264B2_PACKED_MOTION 2
+size_t h264b2_pack_coefs_bound(uint32_t n_coefs);
+int h264b2_pack_coefs(const int16_t *dense, uint32_t n_coefs, void *out, size_t cap, size_t *bytes);
+int h264b2_unpack_coefs(const void *packed, int16_t *dense, uint32_t n_coefs);
+/* Motion records travel the same way: inside every record the 16 vectors of a list are XORed with their predecessor (motion
+ * is far coarser than 4x4: 81 % of the inter macroblocks of the bundled streams carry one vector per list, so 15 of 16 words
+ * become 0), then the records are packed as one int16 stream (1.24 MB -> ~0.4 MB per 1080p picture).  The engine undoes both
+ * steps in HBM (k_expand, k_unmotion).  Bound: h264b2_pack_coefs_bound(n_mbs * 76). */
+int h264b2_pack_motion(const H264B2MbMotion *motion, uint32_t n_mbs, void *out, size_t cap, size_t *bytes);
+int h264b2_unpack_motion(const void *packed, H264B2MbMotion *motion, uint32_t n_mbs);
 
 /* Same, but every array pointer in pics[] is already a device pointer
  * (pre-parsed buffers resident in HBM: the replay path the bench's `value` times). */

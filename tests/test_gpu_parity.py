@@ -52,9 +52,11 @@ def test_full_stream_bit_exact(path):
     eng.close()
 
 
-def test_all_streams_in_one_batch_and_host_submit():
+@pytest.mark.parametrize("packed", [False, True], ids=["plain_arrays", "packed_arrays"])
+def test_all_streams_in_one_batch_and_host_submit(packed):
     """Five different streams share every launch (mixed I/P/B, MBAFF and non-MBAFF pictures in one batch);
-    arrays are passed as HOST pointers through h264b2_submit; frames come back through the async read path."""
+    arrays are passed as HOST pointers through h264b2_submit — with dense coefficient arrays or with the packed
+    transport (h264b2_pack_coefs -> k_expand); frames come back through the async read path."""
     files = golden_files()
     rps = [replay.load_replay(f) for f in files]
     n = len(rps)
@@ -63,7 +65,9 @@ def test_all_streams_in_one_batch_and_host_submit():
     host = eng.pinned_array(n * eng.frame_bytes).reshape(n, eng.frame_bytes)
     for i in range(depth):
         sids = [s for s in range(n) if i < len(rps[s].pictures)]
-        params = [replay.pic_params(rps[s], rps[s].pictures[i]) for s in sids]
+        blobs = [engine.pack_coefs(rps[s].pictures[i].coefs) if packed else None for s in sids]
+        mblobs = [engine.pack_motion(rps[s].pictures[i].motion) if packed and rps[s].pictures[i].motion is not None else None for s in sids]
+        params = [replay.pic_params(rps[s], rps[s].pictures[i], packed_blob=b, packed_motion=m) for s, b, m in zip(sids, blobs, mblobs)]
         eng.submit(sids, params)
         eng.read_pictures_async(sids, [rps[s].pictures[i].dst_surface for s in sids], [host[s].ctypes.data for s in sids])
         eng.sync()
@@ -127,7 +131,14 @@ def _oracle_vs_gpu(rng, wmb, hmb, pics_kwargs, smooth):
             eng.write_picture(0, 0, stale)
             p.deblock_enable = dbk and pic.deblock_enable
             dpb.reconstruct(p, stages)
-            eng.submit([0], [p])
+            # the deblocked pass travels with packed coefficients (incl. I_PCM samples and custom scaling lists)
+            q = p
+            if dbk:
+                blob = engine.pack_coefs(pic.coefs)
+                mblob = engine.pack_motion(pic.motion) if pic.motion is not None else None
+                q = replay.pic_params(rp, pic, packed_blob=blob, packed_motion=mblob)
+                q.deblock_enable = p.deblock_enable
+            eng.submit([0], [q])
             got = eng.read_picture(0, 0)
             if not np.array_equal(got, dpb.surfaces[0]):
                 raise AssertionError(f"{kw} deblock={dbk}: " + _describe(got, dpb.surfaces[0], pic, wmb, hmb))
@@ -188,6 +199,13 @@ def test_error_behaviour():
         eng.submit([0], [p])
     p = replay.pic_params(rp, rp.pictures[0])
     p.width_mbs = 8
+    with pytest.raises(engine.EngineError):
+        eng.submit([0], [p])
+    p = replay.pic_params(rp, rp.pictures[0])
+    p.packed = 1                                     # claims a packed blob, points at dense levels
+    with pytest.raises(engine.EngineError):
+        eng.submit([0], [p])
+    p.packed = 8
     with pytest.raises(engine.EngineError):
         eng.submit([0], [p])
     eng.close()
