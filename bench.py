@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-mode", default="full", choices=["full", "h2d", "d2h"], help="diagnostic: which PCIe legs the e2e loop includes")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--host-layout", default="batch", choices=["batch", "shared"], help="e2e: picture blocks of a submit back to back in pinned memory (one DMA per batch) or one block per distinct picture")
+    ap.add_argument("--host-layout", default="shared", choices=["batch", "shared"], help="e2e: picture blocks of a submit back to back in pinned memory (one DMA per batch) or one block per distinct picture")
     ap.add_argument("--dense-coefs", action="store_true", help="e2e: send plain arrays (dense int16 levels, full motion records) instead of the packed transport")
     ap.add_argument("--no-bitstream", action="store_true", help="skip the Annex-B-in / frames-out pipeline measurement")
     ap.add_argument("--bitstream-streams", type=int, default=32, help="streams per GPU of the Annex-B pipeline measurement")

@@ -19,6 +19,16 @@ __device__ const uint8_t g_tc0_tab[3][52] = {
  {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,1,1,2,2,2,2,3,3,3,4,4,5,5,6,7,8,8,10,11,12,13,15,17},
  {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,1,1,2,2,2,2,3,3,3,4,4,4,5,6,6,7,8,9,10,11,13,14,16,18,20,23,25}};
 
+// thresholds of one (plane, edge kind): alpha, beta and tC0 for bS = 1, 2, 3 (DB:1314-1409) in one word, so the filter's
+// dependent chain holds no table load
+struct DbThr { int alpha, beta; uint32_t tc0; };      // tc0: 3 x 5 bits
+__device__ __forceinline__ uint32_t db_thr_pack(int ia, int ib) {
+    return (uint32_t)g_alpha_tab[ia] | ((uint32_t)g_beta_tab[ib] << 8) | ((uint32_t)g_tc0_tab[0][ia] << 13) | ((uint32_t)g_tc0_tab[1][ia] << 18) | ((uint32_t)g_tc0_tab[2][ia] << 23);
+}
+__device__ __forceinline__ DbThr db_thr_unpack(uint32_t w) {      // packed by k_bs
+    DbThr t; t.alpha = w & 0xff; t.beta = (w >> 8) & 0x1f; t.tc0 = w >> 13; return t;
+}
+
 struct DbCtx { int A, B, left, top, leftflag, dbltop, fieldInFrame, internal, t8; };
 
 __device__ inline DbCtx db_ctx(const PicDev &P, int a, const H264B2MbInfo &I) {   // DB:104-154
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(256) k_bs(const PicDev *pics) {
         // is constant over each 4-sample segment and chroma line k reuses luma line 2k (DB:871-880), so 16 vertical
         // + 16 horizontal values describe the MB.  16 words per MB at bs[a*16]:
         //   [0..1] vertical nibbles (index edge*4 + segment), [2..3] horizontal nibbles,
-        //   [4 + comp*3 + t] thresholds alpha | beta<<8 | indexA<<16 for t = 0 left edge, 1 top edge, 2 internal edges
+        //   [4 + comp*3 + t] thresholds (db_thr_pack: alpha, beta, tC0 of bS 1..3) for t = 0 left edge, 1 top edge, 2 internal edges
         const int dir = lane >> 4, edge = (lane >> 2) & 3, seg = lane & 3;
         const int on = edge == 0 ? (dir ? c.top : c.left) : (c.internal && (!c.t8 || edge == 2));
         const int bS = on ? edge_bs(P, a, 0, dir ? c.B : c.A, !dir, 0, 4 * edge, 4 * seg) : 0;
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(256) k_bs(const PicDev *pics) {
             if (cc) { qq = chroma_qp(P, qq, cc - 1); qp = chroma_qp(P, qp, cc - 1); }
             const int qpav = (qp + qq + 1) >> 1;
             const int ia = clip3i(0, 51, qpav + I.filter_offset_a), ib = clip3i(0, 51, qpav + I.filter_offset_b);
-            rec[4 + lane] = (uint32_t)g_alpha_tab[ia] | ((uint32_t)g_beta_tab[ib] << 8) | ((uint32_t)ia << 16);
+            rec[4 + lane] = db_thr_pack(ia, ib);
         }
         return;
     }

@@ -24,11 +24,6 @@ __device__ __forceinline__ void st_release_flag(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-struct DbThr { int alpha, beta, ia; };
-__device__ __forceinline__ DbThr db_thr_unpack(uint32_t w) {      // packed by k_bs (DB:1314)
-    DbThr t; t.alpha = w & 0xff; t.beta = (w >> 8) & 0xff; t.ia = (w >> 16) & 0xff; return t;
-}
-
 // one sample line: Pw = p3 p2 p1 p0 (byte 3 = p0), Qw = q0 q1 q2 q3 (byte 0 = q0).  DB:1373 / DB:1481.
 __device__ __forceinline__ void filter_words(uint32_t &Pw, uint32_t &Qw, int bS, const DbThr &t, int chroma) {
     const int p0 = Pw >> 24, p1 = (Pw >> 16) & 0xff, p2 = (Pw >> 8) & 0xff, p3 = Pw & 0xff;
@@ -37,7 +32,7 @@ __device__ __forceinline__ void filter_words(uint32_t &Pw, uint32_t &Qw, int bS,
     int np0 = p0, np1 = p1, np2 = p2, nq0 = q0, nq1 = q1, nq2 = q2;
     const int ap = abs(p2 - p0), aq = abs(q2 - q0);
     if (bS < 4) {
-        const int tc0 = g_tc0_tab[bS - 1][t.ia];
+        const int tc0 = (int)((t.tc0 >> (5 * (bS - 1))) & 31u);
         const int tc = chroma ? tc0 + 1 : tc0 + (ap < t.beta) + (aq < t.beta);
         const int delta = clip3i(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
         np0 = clip255(p0 + delta); nq0 = clip255(q0 - delta);
@@ -245,8 +240,7 @@ __device__ inline void deblock_mb_tile(const PicDev &P, int a, int A, int B, int
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int qpav = (q3[i] + qq + 1) >> 1;
-            t3[i]->ia = clip3i(0, 51, qpav + oa);
-            t3[i]->alpha = g_alpha_tab[t3[i]->ia]; t3[i]->beta = g_beta_tab[clip3i(0, 51, qpav + ob)];
+            *t3[i] = db_thr_unpack(db_thr_pack(clip3i(0, 51, qpav + oa), clip3i(0, 51, qpav + ob)));
         }
     }
     const int topf = __any_sync(0xffffffffu, (h & 15u) != 0);

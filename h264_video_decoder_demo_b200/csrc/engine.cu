@@ -478,7 +478,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         class_end(c, 5, sg);
         if (g_inter) {
             class_begin(c, 1, sg);
-            k_inter<<<dim3((c->nmb + 3) / 4, ng), 128, 0, sg>>>(dg);
+            k_inter<<<dim3((c->wmb + 3) / 4, c->hmb, ng), 128, 0, sg>>>(dg);
             class_end(c, 1, sg);
         }
         // boundary strengths need only side info, not samples: compute them before the wavefronts so that the

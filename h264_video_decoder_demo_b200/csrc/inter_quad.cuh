@@ -165,16 +165,18 @@ __device__ __forceinline__ void chroma_quad_pred(const uint8_t *base, int stride
     p[3] = dp4a_uu(__byte_perm(h0, h1, 0x5410), cf, 32) >> 6;
 }
 
-// grid: (ceil(n_mbs / 4), n_pics); block: 128 threads = 4 warps = 4 consecutive macroblock addresses.
+// grid: (ceil(wmb / 4), hmb, n_pics); block: 128 threads = 4 warps = 4 horizontally consecutive macroblocks (no division
+// to find the macroblock: under MBAFF row 2k / 2k+1 are the top / bottom macroblocks of pair row k).
 #ifndef INTER_MIN_BLOCKS
 #define INTER_MIN_BLOCKS 8
 #endif
 __global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *pics) {
     __shared__ InterWarpSmem sm[4];
-    const PicDev &P = pics[blockIdx.y];
+    const PicDev &P = pics[blockIdx.z];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int a = blockIdx.x * 4 + warp;
-    if (!P.motion || a >= P.wmb * P.hmb) return;
+    const int mbx = blockIdx.x * 4 + warp, mby = blockIdx.y;
+    if (!P.motion || mbx >= P.wmb) return;
+    const int a = P.mbaff ? 2 * ((mby >> 1) * P.wmb + mbx) + (mby & 1) : mby * P.wmb + mbx;
     const H264B2MbInfo I = P.info[a];
     if (I.mb_class != H264B2_MB_INTER) return;
     const H264B2MbMotion &M = P.motion[a];
@@ -197,8 +199,7 @@ __global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *p
     }
     const int field = P.mbaff && (I.flags & H264B2_MBF_FIELD);
     const int ys = field ? 2 : 1;
-    int x0, y0;
-    mb_origin(P, a, field, x0, y0);
+    const int x0 = mbx * 16, y0 = !P.mbaff ? mby * 16 : field ? (mby >> 1) * 32 + (mby & 1) : mby * 16;      // mb_origin()
     const int yA = field ? y0 / 2 : y0;                     // IP:577-580
     const int W = P.wmb * 16, H = P.hmb * 16, Wc = W >> 1;
     const unsigned gmask = 0xFFu << (q * 8);
@@ -236,8 +237,10 @@ __global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *p
     {
         uint8_t *Y = P.dst + (size_t)(y0 + (qy + r) * ys) * W + x0 + qx;
         uint32_t o[2];
+        // bi-prediction with w0 = w1 = 2^logWD and a zero offset term IS the default average (IP:2699 with those values)
+        const bool plain = !w.mode || (have0 && have1 && w.w0[0] == w.w1[0] && w.w0[0] == (1 << w.logwd[0]) && ((w.o0[0] + w.o1[0] + 1) >> 1) == 0);
         if (none) { const uint2 t = *(const uint2 *)Y; o[0] = t.x; o[1] = t.y; }
-        else if (!w.mode) {
+        else if (plain) {
 #pragma unroll
             for (int i = 0; i < 2; i++) o[i] = (have0 && have1) ? avg4(pl[0][i], pl[1][i]) : have0 ? pl[0][i] : pl[1][i];
         } else {

@@ -423,6 +423,27 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
     }
     __syncwarp();
     auto above_intra = [&](int x) -> bool { return x >= 0 && x < wmb && ((above[x >> 5] >> (x & 31)) & 1u); };
+    // Side information of the NEXT intra macroblock of this row (residual tile, its own and its neighbours' info records, pred
+    // modes) is pulled into L1 while the current one is reconstructed: none of it is written during this launch, and the
+    // per-macroblock chain (wait -> info -> neighbour info -> residual -> predict) is what bounds this kernel.
+    auto prefetch_mb = [&](int x) {
+        if (GENERIC || x < 0 || x >= wmb) return;
+        const int a = row * wmb + x;
+        const void *p = nullptr;
+        if (lane < 6) p = (const uint8_t *)(P.res + (size_t)a * RES_MB_STRIDE) + lane * 128;
+        else if (lane == 6) p = &P.info[a];
+        else if (lane == 7 && x > 0) p = &P.info[a - 1];
+        else if (lane == 8 && row > 0) p = &P.info[a - wmb + (x + 1 < wmb ? 1 : 0)];
+        else if (lane == 9 && row > 0) p = &P.info[a - wmb - (x > 0 ? 1 : 0)];
+        else if (lane == 10) p = &P.modes[a];
+        if (p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+    };
+    auto next_intra = [&](int x) -> int {          // first intra macroblock of this row after column x, or wmb
+        if (!masks_ok) return wmb;
+        for (int i = x + 1; i < wmb; ) { const uint32_t w = mine[i >> 5] >> (i & 31); if (w) return i + __ffs(w) - 1; i = (i | 31) + 1; }
+        return wmb;
+    };
+    prefetch_mb(next_intra(-1));
     for (int xb = 0; xb < wmb; xb += 32) {
         unsigned mask;
         if (masks_ok) mask = mine[xb >> 5];
@@ -437,6 +458,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
             mask &= mask - 1;
             int need = min(x + 2, wmb);
             if (masks_ok) need = above_intra(x + 1) ? x + 2 : above_intra(x) ? x + 1 : above_intra(x - 1) ? x : 0;
+            prefetch_mb(next_intra(x));
             rs_wait(rs, need, x, lane);
             for (int s = 0; s < per; s++) {
                 const int a = (row * wmb + x) * per + s;
