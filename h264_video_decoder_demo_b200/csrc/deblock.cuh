@@ -50,9 +50,9 @@ __device__ inline DbCtx db_ctx(const PicDev &P, int a, const H264B2MbInfo &I) { 
 
 __device__ __forceinline__ int is_intra_mode(const H264B2MbInfo &I) { return I.mb_class >= H264B2_MB_I4x4 && I.mb_class <= H264B2_MB_I16x16; }   // Q11
 
-__device__ inline int derive_bs(const PicDev &P, int ap, int aq, int xp, int yp, int xq, int yq, int vertical) {   // DB:994
-    const int mbaff = P.mbaff;
-    const H264B2MbInfo Ip = P.info[ap], Iq = P.info[aq];
+template <bool MBAFF>
+__device__ __forceinline__ int derive_bs_core(const PicDev &P, const H264B2MbInfo &Ip, const H264B2MbInfo &Iq, int ap, int aq, int xp, int yp, int xq, int yq, int vertical) {   // DB:994
+    const int mbaff = MBAFF;
     const int fp = (Ip.flags & H264B2_MBF_FIELD) != 0, fq = (Iq.flags & H264B2_MBF_FIELD) != 0;
     const int mixed = mbaff && ap != aq && fp != fq;
     const int intra = is_intra_mode(Ip) || is_intra_mode(Iq);
@@ -91,6 +91,10 @@ __device__ inline int derive_bs(const PicDev &P, int ap, int aq, int xp, int yp,
 #undef FAR
     return 0;
 }
+__device__ inline int derive_bs(const PicDev &P, int ap, int aq, int xp, int yp, int xq, int yq, int vertical) {
+    const H264B2MbInfo Ip = P.info[ap], Iq = P.info[aq];
+    return P.mbaff ? derive_bs_core<true>(P, Ip, Iq, ap, aq, xp, yp, xq, yq, vertical) : derive_bs_core<false>(P, Ip, Iq, ap, aq, xp, yp, xq, yq, vertical);
+}
 
 // p0-side macroblock of sample line k of one edge (DB:742-805) and the bS coordinates (component units)
 __device__ __forceinline__ int edge_p_mb(int a, int nbr, int vertical, int leftflag, int e, int k) {
@@ -107,6 +111,54 @@ __device__ inline int edge_bs(const PicDev &P, int a, int comp, int nbr, int ver
     if (vertical) { xp = xE - 1; if (xp < 0) xp += size; yp = yE; xq = xE; yq = yE; }
     else { xp = xE; yp = (yE - 1) - (yE % 2); if (yp < 0) yp += size; xq = xE; yq = yE - (yE % 2); }
     return derive_bs(P, ap, a, xp * s, yp * s, xq * s, yq * s, vertical);
+}
+
+// Progressive pictures: one warp per macroblock, lane = (direction, edge, 4-sample segment).  2-D grid (no division), the
+// three info records a macroblock's edges can touch are loaded once per warp, and the strength derivation is the
+// frame-only instance of derive_bs_core.  Record layout: see k_bs below.
+__global__ void __launch_bounds__(256) k_bs_prog(const PicDev *pics) {
+    const PicDev &P = pics[blockIdx.z];
+    const int lane = threadIdx.x & 31;
+    const int mbx = blockIdx.x * 8 + (threadIdx.x >> 5), mby = blockIdx.y, wmb = P.wmb;
+    if (mbx >= wmb) return;
+    const int a = mby * wmb + mbx, nmb = wmb * P.hmb;
+    if (!P.deblock_enable || a >= P.deblock_stop || P.generic) return;
+    const H264B2MbInfo I = P.info[a];
+    H264B2MbInfo IA = I, IB = I;
+    int A = -1, B = -1;                                                         // DB:13-69 / PB:2878: same slice, address <= current
+    if (mbx > 0) { IA = P.info[a - 1]; if (IA.slice_number == I.slice_number) A = a - 1; }
+    if (mby > 0) { IB = P.info[a - wmb]; if (IB.slice_number == I.slice_number) B = a - wmb; }
+    const int idc = I.deblock_idc, t8 = (I.flags & H264B2_MBF_T8x8) != 0;
+    const int left = !(mbx == 0 || idc == 1 || (idc == 2 && A < 0)), top = !(mby == 0 || idc == 1 || (idc == 2 && B < 0)), internal = idc != 1;   // DB:104-154
+    const int dir = lane >> 4, edge = (lane >> 2) & 3, seg = lane & 3;
+    const int on = edge == 0 ? (dir ? top : left) : (internal && (!t8 || edge == 2));
+    int bS = 0;
+    if (on) {
+        // DB:639-840 for frame macroblocks: q = this MB at the edge, p = the sample before it (Q14: the MB itself, far side, when
+        // the neighbour is not available)
+        const int nbr = dir ? B : A;
+        const bool outer = edge == 0 && nbr >= 0;
+        const int ap = outer ? nbr : a;
+        const int xq = dir ? 4 * seg : 4 * edge, yq = dir ? 4 * edge : 4 * seg;
+        const int xp = dir ? xq : (edge ? xq - 1 : 15), yp = dir ? (edge ? yq - 1 : 15) : yq;
+        bS = derive_bs_core<false>(P, outer ? (dir ? IB : IA) : I, I, ap, a, xp, yp, xq, yq, !dir);
+    }
+    const int idx = lane & 15;
+    const uint32_t val = (uint32_t)bS << (4 * (idx & 7));
+    const int word = dir * 2 + (idx >> 3);
+    const uint32_t r0 = __reduce_or_sync(0xffffffffu, word == 0 ? val : 0u), r1 = __reduce_or_sync(0xffffffffu, word == 1 ? val : 0u);
+    const uint32_t r2 = __reduce_or_sync(0xffffffffu, word == 2 ? val : 0u), r3 = __reduce_or_sync(0xffffffffu, word == 3 ? val : 0u);
+    uint32_t *rec = P.bs + (size_t)a * 16;
+    if (lane == 0) { *(uint4 *)rec = make_uint4(r0, r1, r2, r3); P.bs[(size_t)nmb * 64 + a] = (r0 | r1 | r2 | r3) != 0; }
+    if (lane < 9 && (r0 | r1 | r2 | r3)) {
+        const int cc = lane / 3, t = lane % 3;
+        int qq = I.mb_class == H264B2_MB_IPCM ? 0 : I.qpy, qp = qq;
+        if (t == 0 && A >= 0) qp = IA.mb_class == H264B2_MB_IPCM ? 0 : IA.qpy;
+        if (t == 1 && B >= 0) qp = IB.mb_class == H264B2_MB_IPCM ? 0 : IB.qpy;
+        if (cc) { qq = chroma_qp(P, qq, cc - 1); qp = chroma_qp(P, qp, cc - 1); }
+        const int qpav = (qp + qq + 1) >> 1;
+        rec[4 + lane] = db_thr_pack(clip3i(0, 51, qpav + I.filter_offset_a), clip3i(0, 51, qpav + I.filter_offset_b));
+    }
 }
 
 // packed layout per MB: word[lane] = vertical edges (4 bit per edge index), word[32+lane] = horizontal

@@ -485,7 +485,8 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         // intra -> deblock chains of the progressive and of the generic (MBAFF) pictures can run side by side
         if (g_deblock) {
             class_begin(c, 3, sg);
-            k_bs<<<dim3((c->nmb + 7) / 8, ng), 256, 0, sg>>>(dg);
+            if (np) k_bs_prog<<<dim3((c->wmb + 7) / 8, c->hmb, np), 256, 0, sg>>>(dg);              // progressive pictures come first in dg
+            if (nq) k_bs<<<dim3((c->nmb + 7) / 8, nq), 256, 0, sg>>>(dg + np);
             class_end(c, 3, sg);
         }
         cudaStream_t sq = sg;
