@@ -53,6 +53,7 @@ __global__ void k_prologue(const uint4 *src, uint4 *dst, int n16, int *progress,
     for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
     for (int i = threadIdx.x; i < nprog; i += blockDim.x) progress[i] = 0;
 }
+__global__ void k_zero_ints(int *p, int n) { for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0; }
 // snapshot n surfaces into the read-back staging buffer (same reason: keep the copy engines for PCIe)
 __global__ void k_snapshot(const uint8_t *const *src, uint8_t *dst, size_t n16) {
     const uint4 *s = (const uint4 *)src[blockIdx.y];
@@ -208,6 +209,9 @@ struct H264B2Context {
     uint8_t **d_ptrs; unsigned long long *d_sums; unsigned long long *h_sums; uint8_t **h_ptrs;
     uint8_t **h_snap[NOUT], **h_snap_dev[NOUT];     // mapped pinned pointer lists for k_snapshot
     uint8_t *bgr; size_t bgr_cap;             // BGR24 output staging
+    // look-ahead (H264B2_LOOKAHEAD, default on): descriptors, unpacking, k_residual and k_bs of batch i+1 need nothing from batch i,
+    // so they run on st_pre while the dependency-bound wavefront kernels of batch i leave issue slots idle; res / bs are double-buffered
+    int lookahead; unsigned batch_no; cudaStream_t st_pre; cudaEvent_t pre_done[DESC_RING], main_done[2];
     size_t bs_stride;                         // words per stream in bs
     // timing
     cudaEvent_t t0, t1;
@@ -312,8 +316,12 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     // per stream: 64 words of strengths per MB + 1 "any strength" word per MB; the stride is rounded to 16 bytes because k_bs
     // writes the records with 16-byte stores (an odd macroblock count would misalign every second stream otherwise)
     c->bs_stride = ((size_t)c->nmb * 65 + 3) & ~(size_t)3;
-    CK(cudaMalloc(&c->bs, (size_t)n_streams * c->bs_stride * 4));
-    CK(cudaMalloc(&c->res, (size_t)n_streams * c->nmb * RES_MB_STRIDE * 2));
+    { const char *e = getenv("H264B2_LOOKAHEAD"); c->lookahead = !(e && atoi(e) == 0); }
+    CK(cudaMalloc(&c->bs, (size_t)n_streams * c->bs_stride * 4 * 2));
+    CK(cudaMalloc(&c->res, (size_t)n_streams * c->nmb * RES_MB_STRIDE * 2 * 2));
+    CK(cudaStreamCreateWithFlags(&c->st_pre, cudaStreamNonBlocking));
+    for (int i = 0; i < DESC_RING; i++) CK(cudaEventCreateWithFlags(&c->pre_done[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->main_done[i], cudaEventDisableTiming));
     c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 4 * MAX_GROUPS;
     {
         const char *g = getenv("H264B2_GROUPS"), *gm = getenv("H264B2_GROUP_MIN");
@@ -372,7 +380,8 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_pull); for (int i = 0; i < NOUT; i++) cudaFreeHost(c->h_snap[i]);
     for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->h2d_done2[i]); cudaEventDestroy(c->compute_done[i]); }
     for (int i = 0; i < NOUT; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
-    for (int i = 0; i < DESC_RING; i++) cudaEventDestroy(c->desc_ev[i]);
+    for (int i = 0; i < DESC_RING; i++) { cudaEventDestroy(c->desc_ev[i]); cudaEventDestroy(c->pre_done[i]); }
+    cudaEventDestroy(c->main_done[0]); cudaEventDestroy(c->main_done[1]); cudaStreamDestroy(c->st_pre);
     cudaFree(c->d_ptrs); cudaFree(c->d_sums); cudaFreeHost(c->h_sums); cudaFreeHost(c->h_ptrs);
     for (int i = 0; i < EV_POOL; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     free(c->ev);
@@ -419,10 +428,12 @@ static int validate(const H264B2Context *c, int n_pics, const int32_t *sids, con
 }
 
 // enqueue the kernels of one batch; every array pointer in pics[] is a device pointer
-static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264B2PicParams *pics, const uint32_t *const *packed = nullptr, const uint32_t *const *packed_motion = nullptr) {
+static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264B2PicParams *pics, const uint32_t *const *packed = nullptr, const uint32_t *const *packed_motion = nullptr,
+                        cudaEvent_t in0 = nullptr, cudaEvent_t in1 = nullptr) {
     const int ring = c->desc_next; c->desc_next = (c->desc_next + 1) % DESC_RING;
     CK(cudaEventSynchronize(c->desc_ev[ring]));
     PicDev *hd = c->h_desc + (size_t)ring * c->n_streams, *dd = c->d_desc + (size_t)ring * c->n_streams;
+    const int par = c->lookahead ? (int)(c->batch_no++ & 1) : 0;
     int any_inter = 0, any_deblock = 0, any_packed = 0, any_packed_motion = 0;
     // descriptors are laid out progressive pictures first, then "generic" ones (MBAFF, or wider than the fast paths
     // support): the wavefront kernels are launched once per kind, each with only its own code path compiled in
@@ -441,8 +452,8 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.ls8 = p.custom_scaling ? p.level_scale8 : c->ls_flat + 2 * 2 * 6 * 16;
         d.stream_base = c->surfaces + (size_t)sids[i] * c->spp * c->frame_bytes;
         d.dst = (uint8_t *)d.stream_base + (size_t)p.dst_surface * c->frame_bytes;
-        d.bs = c->bs + (size_t)sids[i] * c->bs_stride;
-        d.res = c->res + (size_t)sids[i] * c->nmb * RES_MB_STRIDE;
+        d.bs = c->bs + ((size_t)par * c->n_streams + sids[i]) * c->bs_stride;
+        d.res = c->res + ((size_t)par * c->n_streams + sids[i]) * c->nmb * RES_MB_STRIDE;
         d.progress = c->progress + (size_t)sids[i] * 2 * c->hmb;
         d.frame_bytes = c->frame_bytes;
         d.wmb = c->wmb; d.hmb = c->hmb; d.mbaff = p.mbaff_frame_flag; d.cqp0 = p.chroma_qp_offset[0]; d.cqp1 = p.chroma_qp_offset[1];
@@ -453,13 +464,37 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         any_inter |= p.has_inter; any_deblock |= p.deblock_enable;
     }
     int *tickets = c->progress + (c->progress_ints - DESC_RING * 4 * MAX_GROUPS) + ring * 4 * MAX_GROUPS;
-    class_begin(c, 0, c->st);
-    k_prologue<<<1, 256, 0, c->st>>>((const uint4 *)(c->h_desc_dev + (size_t)ring * c->n_streams), (uint4 *)dd, (int)(sizeof(PicDev) * n / 16), c->progress, (int)c->progress_ints);
-    CK(cudaEventRecord(c->desc_ev[ring], c->st));
+    const bool la = c->lookahead != 0;
+    cudaStream_t sp = la ? c->st_pre : c->st;
+    if (la) {
+        if (in0) CK(cudaStreamWaitEvent(sp, in0, 0));
+        if (in1) CK(cudaStreamWaitEvent(sp, in1, 0));
+        CK(cudaStreamWaitEvent(sp, c->main_done[par], 0));       // the res / bs buffers of this parity are free (two batches ago)
+    }
+    class_begin(c, 0, sp);
+    if (la) {
+        k_prologue<<<1, 256, 0, sp>>>((const uint4 *)(c->h_desc_dev + (size_t)ring * c->n_streams), (uint4 *)dd, (int)(sizeof(PicDev) * n / 16), nullptr, 0);
+        k_zero_ints<<<1, 256, 0, c->st>>>(c->progress, (int)c->progress_ints);
+    } else
+        k_prologue<<<1, 256, 0, c->st>>>((const uint4 *)(c->h_desc_dev + (size_t)ring * c->n_streams), (uint4 *)dd, (int)(sizeof(PicDev) * n / 16), c->progress, (int)c->progress_ints);
+    CK(cudaEventRecord(c->desc_ev[ring], sp));
     for (int j = 0; j < n; j++) if (pics[order[j]].clear_surface) CK(cudaMemsetAsync(hd[j].dst, 0, c->frame_bytes, c->st));
-    if (any_packed) k_expand<<<dim3(32, n, any_packed_motion ? 2 : 1), 256, 0, c->st>>>(dd);
-    if (any_packed_motion) k_unmotion<<<dim3((c->nmb * 2 + 255) / 256, n), 256, 0, c->st>>>(dd);
-    class_end(c, 0, c->st);
+    if (any_packed) k_expand<<<dim3(32, n, any_packed_motion ? 2 : 1), 256, 0, sp>>>(dd);
+    if (any_packed_motion) k_unmotion<<<dim3((c->nmb * 2 + 255) / 256, n), 256, 0, sp>>>(dd);
+    class_end(c, 0, sp);
+    if (la) {
+        class_begin(c, 5, sp);
+        k_residual<<<dim3((c->nmb + 7) / 8, n), 256, 0, sp>>>(dd);
+        class_end(c, 5, sp);
+        if (any_deblock) {
+            class_begin(c, 3, sp);
+            if (n_prog) k_bs_prog<<<dim3((c->wmb + 7) / 8, c->hmb, n_prog), 256, 0, sp>>>(dd);
+            if (n - n_prog) k_bs<<<dim3((c->nmb + 7) / 8, n - n_prog), 256, 0, sp>>>(dd + n_prog);
+            class_end(c, 3, sp);
+        }
+        CK(cudaEventRecord(c->pre_done[ring], sp));
+        CK(cudaStreamWaitEvent(c->st, c->pre_done[ring], 0));
+    }
     int G = c->groups;
     while (G > 1 && n / G < c->group_min) G--;
     const int bands = (c->hmb + WF_ROWS - 1) / WF_ROWS;
@@ -473,9 +508,11 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         for (int j = b0; j < b1; j++) { g_inter |= pics[order[j]].has_inter; g_deblock |= pics[order[j]].deblock_enable; }
         const int np = std::max(0, std::min(b1, n_prog) - b0), nq = ng - np;      // progressive / generic pictures of this group
         const PicDev *dg = dd + b0;
-        class_begin(c, 5, sg);
-        k_residual<<<dim3((c->nmb + 7) / 8, ng), 256, 0, sg>>>(dg);
-        class_end(c, 5, sg);
+        if (!la) {
+            class_begin(c, 5, sg);
+            k_residual<<<dim3((c->nmb + 7) / 8, ng), 256, 0, sg>>>(dg);
+            class_end(c, 5, sg);
+        }
         if (g_inter) {
             class_begin(c, 1, sg);
             k_inter<<<dim3((c->wmb + 3) / 4, c->hmb, ng), 128, 0, sg>>>(dg);
@@ -483,7 +520,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         }
         // boundary strengths need only side info, not samples: compute them before the wavefronts so that the
         // intra -> deblock chains of the progressive and of the generic (MBAFF) pictures can run side by side
-        if (g_deblock) {
+        if (g_deblock && !la) {
             class_begin(c, 3, sg);
             if (np) k_bs_prog<<<dim3((c->wmb + 7) / 8, c->hmb, np), 256, 0, sg>>>(dg);              // progressive pictures come first in dg
             if (nq) k_bs<<<dim3((c->nmb + 7) / 8, nq), 256, 0, sg>>>(dg + np);
@@ -519,6 +556,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         if (G > 1) { CK(cudaEventRecord(c->join_ev[g], sg)); CK(cudaStreamWaitEvent(c->st, c->join_ev[g], 0)); }
     }
     (void)any_inter; (void)any_deblock;
+    if (la) CK(cudaEventRecord(c->main_done[par], c->st));
     CK(cudaGetLastError());
     return 0;
 }
@@ -703,7 +741,8 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
     CK(cudaStreamWaitEvent(c->st, c->h2d_done[slot], 0));
     if (c->h2d_streams > 1) { CK(cudaEventRecord(c->h2d_done2[slot], c->st_h2d2)); CK(cudaStreamWaitEvent(c->st, c->h2d_done2[slot], 0)); }
     trace_mark(c, 2, c->st);
-    r = launch_batch(c, n_pics, sids, dev.data(), any_packed ? packed.data() : nullptr, any_packed_m ? packed_m.data() : nullptr);
+    r = launch_batch(c, n_pics, sids, dev.data(), any_packed ? packed.data() : nullptr, any_packed_m ? packed_m.data() : nullptr,
+                     c->h2d_done[slot], c->h2d_streams > 1 ? c->h2d_done2[slot] : nullptr);
     if (r) return r;
     CK(cudaEventRecord(c->compute_done[slot], c->st));
     trace_mark(c, 3, c->st);
@@ -720,10 +759,17 @@ static int surf_ptr(H264B2Context *c, int sid, int surface, uint8_t **p) {
 extern "C" int h264b2_surface_ptr(H264B2Context *c, int sid, int surface, void **dev_ptr) {
     uint8_t *p; int r = surf_ptr(c, sid, surface, &p); if (r) return r; *dev_ptr = p; return 0;
 }
+extern "C" int h264b2_set_lookahead(H264B2Context *c, int on) {
+    if (!c) return fail(-1, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st_pre)); CK(cudaStreamSynchronize(c->st));
+    c->lookahead = on != 0;
+    return 0;
+}
 extern "C" int h264b2_sync(H264B2Context *c) {
     if (!c) return fail(-1, "null context");
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->st_h2d)); CK(cudaStreamSynchronize(c->st_h2d2)); CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_d2h));
+    CK(cudaStreamSynchronize(c->st_h2d)); CK(cudaStreamSynchronize(c->st_h2d2)); CK(cudaStreamSynchronize(c->st_pre)); CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_d2h));
     trace_dump(c);
     return 0;
 }

@@ -39,6 +39,7 @@ _PROTOS = {
     "h264b2_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "h264b2_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "h264b2_sync": (C.c_int, [C.c_void_p]),
+    "h264b2_set_lookahead": (C.c_int, [C.c_void_p, C.c_int]),
     "h264b2_pack_coefs_bound": (C.c_size_t, [C.c_uint32]),
     "h264b2_pack_coefs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "h264b2_unpack_coefs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -233,6 +234,9 @@ class Engine:
         """uint8 numpy view over freshly allocated page-locked memory (freed with the engine's process)."""
         ptr = self.host_alloc(nbytes)
         return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr))
+
+    def set_lookahead(self, on: bool):
+        self._ck(self.lib.h264b2_set_lookahead(self._ctx, 1 if on else 0))
 
     def sync(self):
         self._ck(self.lib.h264b2_sync(self._ctx))

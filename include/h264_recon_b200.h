@@ -218,6 +218,12 @@ int h264b2_dev_copy(H264B2Context *ctx, void *dev_dst, const void *dev_src, size
 int h264b2_host_alloc(H264B2Context *ctx, size_t bytes, void **host_ptr);
 int h264b2_host_free(H264B2Context *ctx, void *host_ptr);
 
+/* Look-ahead (default on; H264B2_LOOKAHEAD=0 in the environment turns it off at creation): descriptor upload, unpacking, the
+ * residual kernel and the boundary-strength kernel of a submit depend on nothing the previous submit produces, so they are
+ * enqueued on a second stream and run while the previous batch's dependency-bound wavefront kernels leave the SMs idle.
+ * on = 0 serialises every kernel on the launch stream (what per-kernel timings and profiles want). */
+int h264b2_set_lookahead(H264B2Context *ctx, int on);
+
 /* Block until all enqueued work is done. */
 int h264b2_sync(H264B2Context *ctx);
 
