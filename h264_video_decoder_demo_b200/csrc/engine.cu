@@ -242,6 +242,38 @@ static void trace_dump(H264B2Context *c) {
     c->trace_n = 0;
 }
 
+// Directional intra modes 3..8 as (index, index, index, kind) tables (layout: pred_tab_px in intra.cuh).  N = 4: neighbours
+// nb[0] corner, nb[1..4] left, nb[5..12] top (PB:1174-1395); N = 8: qa[0] corner, qa[1..8] left, qa[9..24] top (PB:1606-1831).
+static void fill_intra_tables(int N, uint16_t *tab) {
+    const int LB = 1, TB = 1 + N;                      // first left / first top sample
+    auto T = [&](int i) { return i < 0 ? 0 : TB + i; };
+    auto L = [&](int i) { return i < 0 ? 0 : LB + i; };
+    auto e3 = [](int a, int b, int c) { return (uint16_t)(a | (b << 5) | (c << 10)); };
+    auto e2 = [](int a, int b) { return (uint16_t)(a | (b << 5) | (1 << 15)); };
+    auto e1 = [](int a) { return (uint16_t)(a | (a << 5) | (a << 10)); };      // copy: (a + 2a + a + 2) >> 2
+    for (int y = 0; y < N; y++) for (int x = 0; x < N; x++) {
+        uint16_t *o = tab + y * N + x;
+        const int NN = N * N;
+        // 3: diagonal down left
+        o[0 * NN] = (x == N - 1 && y == N - 1) ? e3(T(2 * N - 2), T(2 * N - 1), T(2 * N - 1)) : e3(T(x + y), T(x + y + 1), T(x + y + 2));
+        // 4: diagonal down right
+        o[1 * NN] = x > y ? e3(T(x - y - 2), T(x - y - 1), T(x - y)) : x < y ? e3(L(y - x - 2), L(y - x - 1), L(y - x)) : e3(T(0), 0, L(0));
+        // 5: vertical right
+        { const int z = 2 * x - y, k = x - (y >> 1);
+          o[2 * NN] = (z >= 0 && !(z & 1)) ? e2(T(k - 1), T(k)) : z >= 0 ? e3(T(k - 2), T(k - 1), T(k)) : z == -1 ? e3(L(0), 0, T(0))
+                    : N == 4 ? e3(L(y - 1), L(y - 2), L(y - 3)) : e3(L(y - 2 * x - 1), L(y - 2 * x - 2), L(y - 2 * x - 3)); }
+        // 6: horizontal down
+        { const int z = 2 * y - x, k = y - (x >> 1);
+          o[3 * NN] = (z >= 0 && !(z & 1)) ? e2(L(k - 1), L(k)) : z >= 0 ? e3(L(k - 2), L(k - 1), L(k)) : z == -1 ? e3(L(0), 0, T(0))
+                    : N == 4 ? e3(T(x - 1), T(x - 2), T(x - 3)) : e3(T(x - 2 * y - 1), T(x - 2 * y - 2), T(x - 2 * y - 3)); }
+        // 7: vertical left
+        { const int k = x + (y >> 1); o[4 * NN] = !(y & 1) ? e2(T(k), T(k + 1)) : e3(T(k), T(k + 1), T(k + 2)); }
+        // 8: horizontal up
+        { const int z = x + 2 * y, k = y + (x >> 1), lim = 2 * N - 3;      // 5 for 4x4, 13 for 8x8
+          o[5 * NN] = (z < lim && !(z & 1)) ? e2(L(k), L(k + 1)) : z < lim ? e3(L(k), L(k + 1), L(k + 2)) : z == lim ? e3(L(N - 2), L(N - 1), L(N - 1)) : e1(L(N - 1)); }
+    }
+}
+
 static const uint8_t h_zz4[16] = {0,1,4,8, 5,2,3,6, 9,12,13,10, 7,11,14,15};
 static const uint8_t h_fs4[16] = {0,4,1,8, 12,5,9,13, 2,6,10,14, 3,7,11,15};
 static const uint8_t h_fs8[64] = {
@@ -273,6 +305,9 @@ static int init_tables(H264B2Context *c) {
     uint8_t is4[2][16], is8[2][64];
     for (int k = 0; k < 16; k++) { is4[0][h_zz4[k]] = (uint8_t)k; is4[1][h_fs4[k]] = (uint8_t)k; }
     for (int k = 0; k < 64; k++) { is8[0][zz8[k]] = (uint8_t)k; is8[1][h_fs8[k]] = (uint8_t)k; }
+    { uint16_t t4[6][16], t8[6][64];
+      fill_intra_tables(4, &t4[0][0]); fill_intra_tables(8, &t8[0][0]);
+      CK(cudaMemcpyToSymbol(g_pred4_tab, t4, sizeof t4)); CK(cudaMemcpyToSymbol(g_pred8_tab, t8, sizeof t8)); }
     CK(cudaMemcpyToSymbol(c_iscan4, is4, sizeof is4));
     CK(cudaMemcpyToSymbol(c_iscan8, is8, sizeof is8));
     // Flat_4x4_16 / Flat_8x8_16 LevelScale in list order (PB:4852-4989 with weightScale = 16)

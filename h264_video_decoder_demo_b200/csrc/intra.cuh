@@ -141,6 +141,18 @@ __device__ inline int pred8x8_px(int mode, int x, int y, const int *qa, int topo
     return 0;
 }
 
+// Directional modes 3..8 as data.  Every predicted sample of those modes is (w0*P[i0] + w1*P[i1] + w2*P[i2] + 2) >> 2 over the
+// block's neighbour array P (4x4: nb[0..12]; 8x8: the filtered qa[0..24]) with (w0,w1,w2) = (1,2,1), (2,2,0) — the two-tap
+// average (a+b+1)>>1; a copy is (1,2,1) over one index.  entry = i0 | i1 << 5 | i2 << 10 | two_tap << 15; the host fills the tables at context
+// creation from the same rules as pred4x4_px / pred8x8_px above (fill_intra_tables in engine.cu), and the kernels keep a copy
+// in shared memory: no per-sample switch, no divergence between the samples of a block.
+__device__ uint16_t g_pred4_tab[6][16];
+__device__ uint16_t g_pred8_tab[6][64];
+__device__ __forceinline__ int pred_tab_px(uint32_t e, const int *P) {
+    const int a = P[e & 31], b = P[(e >> 5) & 31], c = P[(e >> 10) & 31];
+    return (e >> 15) ? (a + b + 1) >> 1 : (a + 2 * b + c + 2) >> 2;
+}
+
 // write one reconstructed sample: pred (or, when the reference would have predicted nothing, what the
 // buffer holds — Q15) + residual, clipped.
 __device__ __forceinline__ void put_px(uint8_t *p, int have, int pred, int res) {
@@ -152,7 +164,7 @@ __device__ __forceinline__ void put_px(uint8_t *p, int have, int pred, int res) 
 // the MB itself live in a shared-memory tile for the whole MB (one L2 round trip in, one out); otherwise every
 // sample access goes through the generic MBAFF-aware neighbour derivation.
 template <bool FAST>
-__device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, int lane, IntraWarpSmem &S) {
+__device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, int lane, IntraWarpSmem &S, const uint16_t *tab4, const uint16_t *tab8) {
     const int field = P.mbaff && (I.flags & H264B2_MBF_FIELD);
     const int ys = field ? 2 : 1;
     int x0, y0;
@@ -291,10 +303,20 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
                 if (lane < 25) S.qa[lane] = q;
             }
             __syncwarp();
-            for (int i = lane; i < 64; i += 32) {
-                const int x = i & 7, y = i >> 3;
-                int have; const int pred = pred8x8_px(mode, x, y, S.qa, top16, top16, left8, cav, have);
-                put(0, xO + x, yO + y, have, pred, res[(yO + y) * 16 + xO + x]);
+            if (mode >= 3 && mode <= 8) {
+                const int have = mode == 8 ? left8 : (mode == 3 || mode == 7) ? top16 : (top16 && left8 && cav);
+#pragma unroll
+                for (int i = lane; i < 64; i += 32) {
+                    const int x = i & 7, y = i >> 3;
+                    const int pred = have ? pred_tab_px(tab8[(mode - 3) * 64 + i], S.qa) : 0;
+                    put(0, xO + x, yO + y, have, pred, res[(yO + y) * 16 + xO + x]);
+                }
+            } else {
+                for (int i = lane; i < 64; i += 32) {
+                    const int x = i & 7, y = i >> 3;
+                    int have; const int pred = pred8x8_px(mode, x, y, S.qa, top16, top16, left8, cav, have);
+                    put(0, xO + x, yO + y, have, pred, res[(yO + y) * 16 + xO + x]);
+                }
             }
             __syncwarp();
         }
@@ -310,7 +332,13 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
             __syncwarp();
             if (lane < 16) {
                 const int x = lane & 3, y = lane >> 2;
-                int have; const int pred = pred4x4_px(mode, x, y, S.nb, have);
+                int have, pred;
+                if (mode >= 3 && mode <= 8) {
+                    const int topok = S.nb[5] >= 0 && S.nb[6] >= 0 && S.nb[7] >= 0 && S.nb[8] >= 0, trok = S.nb[9] >= 0 && S.nb[10] >= 0 && S.nb[11] >= 0 && S.nb[12] >= 0;
+                    const int leftok = S.nb[1] >= 0 && S.nb[2] >= 0 && S.nb[3] >= 0 && S.nb[4] >= 0, cornok = S.nb[0] >= 0;
+                    have = mode == 8 ? leftok : (mode == 3 || mode == 7) ? (topok && trok) : (topok && leftok && cornok);
+                    pred = have ? pred_tab_px(tab4[(mode - 3) * 16 + lane], S.nb) : 0;
+                } else pred = pred4x4_px(mode, x, y, S.nb, have);
                 put(0, xO + x, yO + y, have, pred, res[(yO + y) * 16 + xO + x]);
             }
             __syncwarp();
@@ -393,7 +421,9 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
     __shared__ int s_prog[WF_ROWS];
     __shared__ uint32_t s_mask[WF_ROWS][2][8];
     __shared__ int s_ticket;
+    __shared__ uint16_t s_tab4[6 * 16], s_tab8[6 * 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) { s_tab8[i] = (&g_pred8_tab[0][0])[i]; if (i < 6 * 16) s_tab4[i] = (&g_pred4_tab[0][0])[i]; }
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
     if (threadIdx.x < WF_ROWS) s_prog[threadIdx.x] = 0;
     __syncthreads();
@@ -464,7 +494,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
                 const int a = (row * wmb + x) * per + s;
                 const H264B2MbInfo I = P.info[a];
                 if (I.mb_class >= H264B2_MB_I4x4 && I.mb_class <= H264B2_MB_IPCM) {
-                    if (!GENERIC || intra_fast_ok(P, a)) intra_mb<true>(P, a, I, lane, sm[warp]); else intra_mb<false>(P, a, I, lane, sm[warp]);
+                    if (!GENERIC || intra_fast_ok(P, a)) intra_mb<true>(P, a, I, lane, sm[warp], s_tab4, s_tab8); else intra_mb<false>(P, a, I, lane, sm[warp], s_tab4, s_tab8);
                 }
             }
             rs_publish(rs, x + 1, lane);
