@@ -305,10 +305,11 @@ template <bool GENERIC>
 __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_deblock(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ DbTile tiles[WF_ROWS];
     __shared__ int s_prog[WF_ROWS];
+    __shared__ uint64_t s_bar[WF_ROWS];
     __shared__ int s_ticket;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
-    if (threadIdx.x < WF_ROWS) s_prog[threadIdx.x] = 0;
+    if (threadIdx.x < WF_ROWS) { s_prog[threadIdx.x] = 0; mbar_init(&s_bar[threadIdx.x], 1); }
     __syncthreads();
     const int t = s_ticket;
     if (t >= npics * bands) return;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_deblock(const
     const int per = P.mbaff ? 2 : 1;
     const int rows = P.hmb / per, wmb = P.wmb, nmb = P.wmb * P.hmb;
     if (row >= rows) return;
-    RowSync rs = rs_init(s_prog, warp, row, rows, P.progress + P.hmb, wmb);     // progress[1][row]
+    RowSync rs = rs_init(s_prog, s_bar, warp, row, rows, P.progress + P.hmb, wmb);     // progress[1][row]
     if (!GENERIC) { deblock_row_fast(P, row, lane, tiles[warp], rs); return; }
     const uint32_t *anyflag = P.bs + (size_t)nmb * 64;
     for (int xb = 0; xb < wmb; xb += 32) {

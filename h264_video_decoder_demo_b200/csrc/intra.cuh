@@ -419,13 +419,14 @@ template <bool GENERIC>
 __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ IntraWarpSmem sm[WF_ROWS];
     __shared__ int s_prog[WF_ROWS];
+    __shared__ uint64_t s_bar[WF_ROWS];
     __shared__ uint32_t s_mask[WF_ROWS][2][8];
     __shared__ int s_ticket;
     __shared__ uint16_t s_tab4[6 * 16], s_tab8[6 * 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) { s_tab8[i] = (&g_pred8_tab[0][0])[i]; if (i < 6 * 16) s_tab4[i] = (&g_pred4_tab[0][0])[i]; }
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
-    if (threadIdx.x < WF_ROWS) s_prog[threadIdx.x] = 0;
+    if (threadIdx.x < WF_ROWS) { s_prog[threadIdx.x] = 0; mbar_init(&s_bar[threadIdx.x], 1); }
     __syncthreads();
     const int t = s_ticket;
     if (t >= npics * bands) return;
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
     const int per = P.mbaff ? 2 : 1;
     const int rows = P.hmb / per, wmb = P.wmb;
     if (row >= rows) return;
-    RowSync rs = rs_init(s_prog, warp, row, rows, P.progress, wmb);      // progress[0][row]
+    RowSync rs = rs_init(s_prog, s_bar, warp, row, rows, P.progress, wmb);      // progress[0][row]
     // Intra masks of this row and of the row above.  An intra MB only has to wait for the row above if one of its
     // neighbours B, C, D there is itself intra: inter neighbours were completed by k_inter before this kernel
     // started.  In P/B pictures, where intra MBs are scattered, this removes the false chains a plain

@@ -29,7 +29,29 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// Waiting inside a band: the waiting warp parks on an mbarrier (one per row, completed by every publish of that row) instead
+// of polling the shared counter — ncu showed two thirds of k_intra's executed instructions in the nanosleep poll loop.  The
+// counter stays the source of truth: the waiter re-reads it after every wake-up (mbarrier.try_wait also returns after a
+// hardware time limit, so a stale phase guess costs a delay, never a hang).
+#ifndef WF_MBAR
+#define WF_MBAR 0
+#endif
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ int mbar_try_wait(uint32_t bar, int parity) {
+    int ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.s32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+
 struct RowSync {
+    uint32_t bar_above, bar_mine;   // mbarriers (shared addresses) of the row above / of this row
+    int phase;                      // completed phases of bar_above this warp has consumed (its parity is what matters)
     volatile int *s_above;   // shared counter of the row above (same band), or nullptr
     volatile int *s_mine;    // shared counter of this row
     int *g_above;            // global counter of the row above (other band), or nullptr when this is row 0
@@ -38,8 +60,9 @@ struct RowSync {
     int width;
 };
 
-__device__ __forceinline__ RowSync rs_init(int *s_prog, int warp, int row, int rows, int *g_prog, int width) {
+__device__ __forceinline__ RowSync rs_init(int *s_prog, uint64_t *s_bar, int warp, int row, int rows, int *g_prog, int width) {
     RowSync r;
+    r.bar_mine = smem_addr(s_bar + warp); r.bar_above = warp > 0 ? smem_addr(s_bar + warp - 1) : 0; r.phase = 0;
     r.s_mine = s_prog + warp;
     r.s_above = warp > 0 ? s_prog + warp - 1 : nullptr;
     r.g_above = (warp == 0 && row > 0) ? g_prog + row - 1 : nullptr;
@@ -55,6 +78,7 @@ __device__ __forceinline__ void rs_publish(RowSync &r, int v, int lane) {
     __syncwarp();
     if (lane == 0) {
         *r.s_mine = v;
+        if (WF_MBAR) mbar_arrive(r.bar_mine);
         if (r.g_mine) st_release_gpu(r.g_mine, v);
     }
 }
@@ -64,9 +88,13 @@ __device__ __forceinline__ void rs_wait(RowSync &r, int need, int mine, int lane
     if (r.seen >= need) return;
     if (lane == 0) {
         *r.s_mine = mine;                          // nothing of ours is pending: everything left of `mine` was published with a fence
+        if (WF_MBAR) mbar_arrive(r.bar_mine);
         if (r.g_mine) st_release_gpu(r.g_mine, mine);
         int s;
-        if (r.s_above) { while ((s = *r.s_above) < need) __nanosleep(WF_POLL_NS); }
+        if (r.s_above) {
+            if (WF_MBAR) { while ((s = *r.s_above) < need) r.phase += mbar_try_wait(r.bar_above, r.phase & 1); }
+            else { while ((s = *r.s_above) < need) __nanosleep(WF_POLL_NS); }
+        }
         else { while ((s = ld_relaxed_flag(r.g_above)) < need) __nanosleep(2 * WF_POLL_NS); __threadfence(); }
         r.seen = s;
     }
