@@ -34,7 +34,7 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v) {
 // counter stays the source of truth: the waiter re-reads it after every wake-up (mbarrier.try_wait also returns after a
 // hardware time limit, so a stale phase guess costs a delay, never a hang).
 #ifndef WF_MBAR
-#define WF_MBAR 0
+#define WF_MBAR 1
 #endif
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
