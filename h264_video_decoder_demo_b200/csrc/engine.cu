@@ -609,38 +609,49 @@ extern "C" size_t h264b2_pack_coefs_bound(uint32_t n_coefs) {
     const size_t nc = ((size_t)n_coefs + 15) / 16, ng = (nc + 31) / 32;
     return (16 + ng * 4 + ((nc + 1) & ~(size_t)1) * 2 + nc * 32 + 15) & ~(size_t)15;
 }
-extern "C" int h264b2_pack_coefs(const int16_t *dense, uint32_t n_coefs, void *out, size_t cap, size_t *bytes) {
-    if ((!dense && n_coefs) || !out || !bytes || ((uintptr_t)out & 3)) return fail(-1, "pack_coefs: bad argument");
-    const size_t nc = ((size_t)n_coefs + 15) / 16, ng = (nc + 31) / 32;
-    const size_t fixed = 16 + ng * 4 + ((nc + 1) & ~(size_t)1) * 2;
-    if (cap < fixed) return fail(-3, "pack_coefs: output buffer too small");
-    uint32_t *hdr = (uint32_t *)out, *base = hdr + 4;
-    uint16_t *map = (uint16_t *)(base + ng);
-    int16_t *val = (int16_t *)((uint8_t *)out + fixed);
-    const size_t vcap = (cap - fixed) / 2;
-    size_t nv = 0;
-    if (nc & 1) map[nc] = 0;
-    for (size_t ch = 0; ch < nc; ch++) {
+// streaming writer of the blob: chunks of 16 levels arrive in order (the motion packer produces them four records at a time)
+struct BlobWriter {
+    uint32_t *hdr, *base; uint16_t *map; int16_t *val; size_t nc, fixed, vcap, nv = 0, ch = 0; bool overflow = false;
+    bool begin(void *out, size_t cap, size_t n_levels) {
+        nc = (n_levels + 15) / 16;
+        const size_t ng = (nc + 31) / 32;
+        fixed = 16 + ng * 4 + ((nc + 1) & ~(size_t)1) * 2;
+        if (cap < fixed) return false;
+        hdr = (uint32_t *)out; base = hdr + 4; map = (uint16_t *)(base + ng); val = (int16_t *)((uint8_t *)out + fixed);
+        vcap = (cap - fixed) / 2;
+        if (nc & 1) map[nc] = 0;
+        return true;
+    }
+    inline void chunk(const int16_t *c, size_t n) {          // n = 16 except for the tail chunk
         if ((ch & 31) == 0) base[ch >> 5] = (uint32_t)nv;
-        const size_t lo = ch * 16, hi = std::min<size_t>(lo + 16, n_coefs);
-        if (nv + 16 > vcap) {          // exact check only when space is short
-            size_t cnt = 0; for (size_t k = lo; k < hi; k++) cnt += dense[k] != 0;
-            if (nv + cnt > vcap) return fail(-3, "pack_coefs: output buffer too small");
+        if (n == 16) {                                       // most chunks hold nothing: test 32 bytes at once
+            uint64_t q[4]; memcpy(q, c, 32);
+            if (!(q[0] | q[1] | q[2] | q[3])) { map[ch++] = 0; return; }
+        }
+        if (nv + 16 > vcap) {                                // exact check only when space is short
+            size_t cnt = 0; for (size_t k = 0; k < n; k++) cnt += c[k] != 0;
+            if (nv + cnt > vcap) { overflow = true; map[ch++] = 0; return; }
         }
         uint32_t bm = 0;
-        if (hi - lo == 16) {               // most chunks hold nothing: test 32 bytes at once
-            uint64_t q[4]; memcpy(q, dense + lo, 32);
-            if (!(q[0] | q[1] | q[2] | q[3])) { map[ch] = 0; continue; }
-        }
-        for (size_t k = lo; k < hi; k++) { const int16_t v = dense[k]; val[nv] = v; const unsigned nz = v != 0; bm |= nz << (k - lo); nv += nz; }
-        map[ch] = (uint16_t)bm;
+        for (size_t k = 0; k < n; k++) { const int16_t v = c[k]; val[nv] = v; const unsigned nz = v != 0; bm |= nz << k; nv += nz; }
+        map[ch++] = (uint16_t)bm;
     }
-    size_t total = fixed + nv * 2;
-    while (total & 15) { if (total + 2 <= cap) *(int16_t *)((uint8_t *)out + total) = 0; total += 2; }
-    if (total > cap) return fail(-3, "pack_coefs: output buffer too small");
-    hdr[0] = H264B2_PACK_MAGIC; hdr[1] = (uint32_t)nc; hdr[2] = (uint32_t)nv; hdr[3] = (uint32_t)total;
-    *bytes = total;
-    return 0;
+    int end(size_t cap, size_t *bytes) {
+        if (overflow) return -3;
+        size_t total = fixed + nv * 2;
+        while (total & 15) { if (total + 2 <= cap) *(int16_t *)((uint8_t *)hdr + total) = 0; total += 2; }
+        if (total > cap) return -3;
+        hdr[0] = H264B2_PACK_MAGIC; hdr[1] = (uint32_t)nc; hdr[2] = (uint32_t)nv; hdr[3] = (uint32_t)total;
+        *bytes = total;
+        return 0;
+    }
+};
+extern "C" int h264b2_pack_coefs(const int16_t *dense, uint32_t n_coefs, void *out, size_t cap, size_t *bytes) {
+    if ((!dense && n_coefs) || !out || !bytes || ((uintptr_t)out & 3)) return fail(-1, "pack_coefs: bad argument");
+    BlobWriter w;
+    if (!w.begin(out, cap, n_coefs)) return fail(-3, "pack_coefs: output buffer too small");
+    for (size_t lo = 0; lo < n_coefs; lo += 16) w.chunk(dense + lo, std::min<size_t>(16, n_coefs - lo));
+    return w.end(cap, bytes) ? fail(-3, "pack_coefs: output buffer too small") : 0;
 }
 extern "C" int h264b2_unpack_coefs(const void *packed, int16_t *dense, uint32_t n_coefs) {
     const uint32_t *hdr = (const uint32_t *)packed;
@@ -654,12 +665,21 @@ extern "C" int h264b2_unpack_coefs(const void *packed, int16_t *dense, uint32_t 
 }
 
 extern "C" int h264b2_pack_motion(const H264B2MbMotion *motion, uint32_t n_mbs, void *out, size_t cap, size_t *bytes) {
-    if ((!motion && n_mbs) || !out || !bytes) return fail(-1, "pack_motion: bad argument");
-    std::vector<uint32_t> tmp((size_t)n_mbs * (sizeof(H264B2MbMotion) / 4));
-    if (n_mbs) memcpy(tmp.data(), motion, (size_t)n_mbs * sizeof(H264B2MbMotion));
-    for (size_t a = 0; a < n_mbs; a++)
-        for (int l = 0; l < 2; l++) { uint32_t *w = tmp.data() + a * (sizeof(H264B2MbMotion) / 4) + l * 16; for (int r = 15; r >= 1; r--) w[r] ^= w[r - 1]; }
-    return h264b2_pack_coefs((const int16_t *)tmp.data(), (uint32_t)(n_mbs * (sizeof(H264B2MbMotion) / 2)), out, cap, bytes);
+    if ((!motion && n_mbs) || !out || !bytes || ((uintptr_t)out & 3)) return fail(-1, "pack_motion: bad argument");
+    constexpr size_t W = sizeof(H264B2MbMotion) / 4, H16 = sizeof(H264B2MbMotion) / 2;      // 38 words = 76 int16 per record
+    BlobWriter w;
+    if (!w.begin(out, cap, (size_t)n_mbs * H16)) return fail(-3, "pack_motion: output buffer too small");
+    // four records = 304 int16 = 19 whole chunks: XOR-chain them in a small buffer and hand the chunks on
+    uint32_t buf[4 * W];
+    for (size_t a = 0; a < n_mbs; a += 4) {
+        const size_t n = std::min<size_t>(4, n_mbs - a);
+        memcpy(buf, motion + a, n * sizeof(H264B2MbMotion));
+        for (size_t k = 0; k < n; k++)
+            for (int l = 0; l < 2; l++) { uint32_t *q = buf + k * W + l * 16; for (int r = 15; r >= 1; r--) q[r] ^= q[r - 1]; }
+        const int16_t *c = (const int16_t *)buf;
+        for (size_t lo = 0; lo < n * H16; lo += 16) w.chunk(c + lo, std::min<size_t>(16, n * H16 - lo));
+    }
+    return w.end(cap, bytes) ? fail(-3, "pack_motion: output buffer too small") : 0;
 }
 extern "C" int h264b2_unpack_motion(const void *packed, H264B2MbMotion *motion, uint32_t n_mbs) {
     int r = h264b2_unpack_coefs(packed, (int16_t *)motion, (uint32_t)(n_mbs * (sizeof(H264B2MbMotion) / 2)));
