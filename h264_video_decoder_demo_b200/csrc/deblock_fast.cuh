@@ -25,7 +25,10 @@ __device__ __forceinline__ void st_release_flag(int *p, int v) {
 }
 
 // one sample line: Pw = p3 p2 p1 p0 (byte 3 = p0), Qw = q0 q1 q2 q3 (byte 0 = q0).  DB:1373 / DB:1481.
-__device__ __forceinline__ void filter_words(uint32_t &Pw, uint32_t &Qw, int bS, const DbThr &t, int chroma) {
+#ifndef DB_FILTER_NOINLINE
+#define DB_FILTER_NOINLINE 0
+#endif
+__device__ __forceinline__ void filter_words_body(uint32_t &Pw, uint32_t &Qw, int bS, const DbThr &t, int chroma) {
     const int p0 = Pw >> 24, p1 = (Pw >> 16) & 0xff, p2 = (Pw >> 8) & 0xff, p3 = Pw & 0xff;
     const int q0 = Qw & 0xff, q1 = (Qw >> 8) & 0xff, q2 = (Qw >> 16) & 0xff, q3 = Qw >> 24;
     if (!(abs(p0 - q0) < t.alpha && abs(p1 - p0) < t.beta && abs(q1 - q0) < t.beta)) return;
@@ -47,6 +50,23 @@ __device__ __forceinline__ void filter_words(uint32_t &Pw, uint32_t &Qw, int bS,
     }
     Pw = (uint32_t)p3 | ((uint32_t)np2 << 8) | ((uint32_t)np1 << 16) | ((uint32_t)np0 << 24);
     Qw = (uint32_t)nq0 | ((uint32_t)nq1 << 8) | ((uint32_t)nq2 << 16) | ((uint32_t)q3 << 24);
+}
+
+// ONE copy of the filter in the kernel (DB_FILTER_NOINLINE=1): k_deblock's eight inlined copies were 44 KB of SASS and ncu showed
+// instruction-fetch stalls; the call passes everything in registers (packed words in, packed words out).
+__device__ __noinline__ uint2 filter_words_call(uint32_t Pw, uint32_t Qw, int bS, uint32_t thr, int chroma) {
+    const DbThr t = db_thr_unpack(thr);
+    filter_words_body(Pw, Qw, bS, t, chroma);
+    return make_uint2(Pw, Qw);
+}
+__device__ __forceinline__ uint32_t db_thr_repack(const DbThr &t) { return (uint32_t)t.alpha | ((uint32_t)t.beta << 8) | (t.tc0 << 13); }
+__device__ __forceinline__ void filter_words(uint32_t &Pw, uint32_t &Qw, int bS, const DbThr &t, int chroma) {
+#if DB_FILTER_NOINLINE
+    const uint2 r = filter_words_call(Pw, Qw, bS, db_thr_repack(t), chroma);
+    Pw = r.x; Qw = r.y;
+#else
+    filter_words_body(Pw, Qw, bS, t, chroma);
+#endif
 }
 
 // vertical phase on the staged tile: lane = sample row; step i filters the edge between tile words i and i+1

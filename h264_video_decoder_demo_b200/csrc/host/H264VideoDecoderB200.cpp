@@ -157,7 +157,7 @@ int CH264VideoDecoderB200::open_bitstream(const char *url) {
     pc.ctx = ctx;
     if (h264b2_host_alloc(ctx, (size_t)wmb * hmb * 384, (void **)&frame)) FAIL(-3, "open: %s", h264b2_last_error());
     if (h264b2_front_create(&fe, pin_alloc, pin_free, &pc) || h264b2_front_open_file(fe, url)) FAIL(-1, "open: %s", fe ? h264b2_front_last_error(fe) : "out of memory");
-    h264b2_front_set_packed(fe, getenv("H264B2_PLAIN_ARRAYS") ? 0 : (H264B2_PACKED_COEFS | H264B2_PACKED_MOTION));      // packed levels and motion over PCIe unless told otherwise
+    h264b2_front_set_packed(fe, getenv("H264B2_PACKED_ARRAYS") ? (H264B2_PACKED_COEFS | H264B2_PACKED_MOTION) : 0);      // H264B2_PACKED_ARRAYS=1: packed levels and motion over PCIe. Off by default: this path is bound by the host parser (~70 pictures/s/thread, < 1 GB/s of PCIe), and packing costs it 1.5 ms per picture; it pays when submits run at > 10k pictures/s (bench e2e)
     producer = std::thread([&] {
         for (;;) {
             H264B2FrontEvent e;

@@ -87,7 +87,7 @@ extern "C" int h264b2_multi_decode(int device, int n_inputs, const char *const *
     for (int s = 0; s < n_streams; s++) {
         const std::vector<uint8_t> &v = bufs[buf_of[st[s].owner]];
         if (h264b2_front_create(&st[s].fe, pin_alloc, pin_free, &pin) || h264b2_front_open_range(st[s].fe, v.data(), v.size(), st[s].begin, st[s].end, st[s].more_follows)) { first_error = st[s].fe ? h264b2_front_last_error(st[s].fe) : "out of memory"; break; }
-        h264b2_front_set_packed(st[s].fe, getenv("H264B2_PLAIN_ARRAYS") ? 0 : (H264B2_PACKED_COEFS | H264B2_PACKED_MOTION));      // packed levels and motion over PCIe unless told otherwise
+        h264b2_front_set_packed(st[s].fe, getenv("H264B2_PACKED_ARRAYS") ? (H264B2_PACKED_COEFS | H264B2_PACKED_MOTION) : 0);      // H264B2_PACKED_ARRAYS=1: packed levels and motion over PCIe. Off by default: this path is bound by the host parser (~70 pictures/s/thread, < 1 GB/s of PCIe), and packing costs it 1.5 ms per picture; it pays when submits run at > 10k pictures/s (bench e2e)
     }
     H264B2MultiStats S; memset(&S, 0, sizeof S);
     S.threads = n_threads; S.streams = n_inputs; S.units = n_streams; S.width_mbs = wmb; S.height_mbs = hmb;
