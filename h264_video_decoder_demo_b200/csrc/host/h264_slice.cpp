@@ -1087,7 +1087,7 @@ struct Dec {
         if (cabac) {
             if ((unsigned)sh.cabac_init_idc > 2) return -1;      // non-conforming (the reference goes on with uninitialised contexts, H264Cabac.cpp:41)
             while (!br.aligned()) br.u1();
-            cb.init_contexts(st, sh.cabac_init_idc, sh.SliceQPY); cb.init_engine(&br);
+            cb.init_contexts(st, sh.cabac_init_idc, sh.SliceQPY); cb.start_slice(&br);
         }
         if (!mbaff) F.mb_field = sh.field_pic_flag;
         cur = sh.first_mb_in_slice * (1 + mbaff);
