@@ -129,7 +129,7 @@ extern uint8_t g_next_state[2][128];      // [0 = MPS decoded, 1 = LPS decoded][
 struct Cabac {
     BitReader *br = nullptr;
     uint32_t range = 0, offset = 0;
-    uint8_t state[1024];          // (pStateIdx << 1) | valMPS
+    uint8_t state[1024];          // (pStateIdx << 1) | valMPS; 16 bit on purpose: a byte store may alias range / offset / win and would force them through memory after every decision
     void init_contexts(int slice_type, int cabac_init_idc, int slice_qp);
     // The arithmetic decoder pulls its bits from a 64-bit window that is refilled 32 bits at a time (BitReader::peek is a pure
     // function of the position, past-the-end behaviour included, so reading ahead changes nothing); br->pos runs `avail` bits

@@ -51,19 +51,24 @@ struct Dec {
         n = c - W + 1; nC_ = (n < 0 || col == W - 1 || !same_slice(n, c)) ? -1 : n;
         n = c - W - 1; nD_ = (n < 0 || col == 0 || !same_slice(n, c)) ? -1 : n;
     }
-    Nb nbr(int c, int xN, int yN, bool chroma) const {
+    // progressive pictures: four cached addresses and two masks — kept inline, it is called ~30 times per macroblock
+    __attribute__((always_inline)) inline Nb nbr(int c, int xN, int yN, bool chroma) const {
+        if (mbaff) return nbr_mbaff(c, xN, yN, chroma);
         const int maxW = chroma ? 8 : 16, maxH = chroma ? 8 : 16;
         Nb r; r.mb = -1; r.xW = 0; r.yW = 0;
         if (yN > maxH - 1) return r;
-        if (!mbaff) {
-            if (c != nc_mb || mbs[c].slice != nc_slice) nbr_cache(c);
-            int n;
-            if (xN < 0) n = yN < 0 ? nD_ : nA_;
-            else if (xN <= maxW - 1) n = yN < 0 ? nB_ : c;
-            else n = yN < 0 ? nC_ : -1;
-            r.mb = n; r.xW = (xN + maxW) & (maxW - 1); r.yW = (yN + maxH) & (maxH - 1);
-            return r;
-        }
+        if (c != nc_mb || mbs[c].slice != nc_slice) nbr_cache(c);
+        int n;
+        if (xN < 0) n = yN < 0 ? nD_ : nA_;
+        else if (xN <= maxW - 1) n = yN < 0 ? nB_ : c;
+        else n = yN < 0 ? nC_ : -1;
+        r.mb = n; r.xW = (xN + maxW) & (maxW - 1); r.yW = (yN + maxH) & (maxH - 1);
+        return r;
+    }
+    __attribute__((noinline)) Nb nbr_mbaff(int c, int xN, int yN, bool chroma) const {
+        const int maxW = chroma ? 8 : 16, maxH = chroma ? 8 : 16;
+        Nb r; r.mb = -1; r.xW = 0; r.yW = 0;
+        if (yN > maxH - 1) return r;
         // MBAFF (Table 6-4)
         int A = 2 * (c / 2 - 1), B = 2 * (c / 2 - W), C = 2 * (c / 2 - W + 1), D = 2 * (c / 2 - W - 1);
         if (A < 0 || A > c || !same_slice(A, c) || (c / 2) % W == 0) A = -2;
