@@ -250,6 +250,7 @@ def main():
             store, blobs, mblobs, host_params, o = eng.pinned_array(bound), [], [], [], 0
             o += (-store.ctypes.data) % 64
             extents = []
+            t_pack = 0.0
             for pic in rpv.pictures:
                 ptrs, o0, mblob = {}, o, None
                 for k in names:
@@ -259,14 +260,18 @@ def main():
                     if k == "motion":
                         if not pic.has_inter:
                             continue
+                        t0p = time.perf_counter()
                         mblob = engine.pack_motion(a, store[o:o + mb_(pic)])
+                        t_pack += time.perf_counter() - t0p
                         ptrs[k] = mblob.ctypes.data
                         o += al(mblob.size)
                         continue
                     store[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
                     ptrs[k] = store.ctypes.data + o
                     o += al(a.nbytes)
+                t0p = time.perf_counter()
                 b = engine.pack_coefs(pic.coefs, store[o:o + cb(pic)])
+                t_pack += time.perf_counter() - t0p
                 o += al(b.size)
                 blobs.append(b)
                 mblobs.append(mblob)
@@ -276,6 +281,7 @@ def main():
         else:
             host_params = [replay.pic_params(rpv, pic) for pic in rpv.pictures]
         variants.append({"rp": rpv, "host_params": host_params, "_store": store if blobs else None, "extents": extents if blobs else None, "blobs": blobs, "mblobs": mblobs if blobs else None,
+                         "pack_ms": (1000.0 * t_pack / max(1, len(rpv.pictures))) if blobs else None,
                          "host_bytes": [e[1] for e in extents] if blobs else [pic.nbytes() for pic in rpv.pictures], "rs": None})
     sids = list(range(S))
     var_of = [s % len(variants) for s in sids]
@@ -445,6 +451,8 @@ def main():
         e2e_kt = eng.kernel_times()
         e2e = {"value": round(S * npic * args.e2e_steps * world / t1, 1), "unit": UNIT,
                "h2d_bytes_per_step": int(sum(variants[var_of[s]]["host_bytes"][pic_of(s, i)] for s in sids for i in range(npic))),
+               "host_pack_ms_per_picture": None if args.dense_coefs else round(max(v["pack_ms"] for v in variants), 3),
+               "host_pack_note": "h264b2_pack_coefs + h264b2_pack_motion on one host core, done once per picture by the host stage BEFORE the timed region (the timed region starts at the C-ABI call)",
                "host_layout": host_layout, "arrays": "plain (dense int16 levels, 152-byte motion records)" if args.dense_coefs else "packed levels and motion records (h264b2_pack_coefs / h264b2_pack_motion)",
                "d2h_bytes_per_step": int(npic * S * eng.frame_bytes),
                "steps": args.e2e_steps, "device_ms_per_step": round(e2e_dev_ms / args.e2e_steps, 1),
