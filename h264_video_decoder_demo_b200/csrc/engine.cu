@@ -692,6 +692,12 @@ extern "C" int h264b2_unpack_motion(const void *packed, H264B2MbMotion *motion, 
 // ---- host-array submit: one DMA per contiguous span, straight from the caller's memory (pinned memory
 // from h264b2_host_alloc makes the copies asynchronous; pageable memory works but is staged by the driver).
 struct Span { const uint8_t *p; size_t n; const void **slot; };
+// header of a packed blob: magic, chunk count as expected, and a total size that matches the value count
+static inline bool blob_header_ok(const uint32_t *hdr, uint32_t want_chunks) {
+    if (((uintptr_t)hdr & 15) || hdr[0] != H264B2_PACK_MAGIC || hdr[1] != want_chunks) return false;
+    const size_t nc = hdr[1], ng = (nc + 31) / 32, fixed = 16 + ng * 4 + ((nc + 1) & ~(size_t)1) * 2;
+    return hdr[2] <= nc * 16 && hdr[3] == ((fixed + (size_t)hdr[2] * 2 + 15) & ~(size_t)15);
+}
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, const H264B2PicParams *pics) {
@@ -715,14 +721,14 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
         if ((p.packed & H264B2_PACKED_MOTION) && p.has_inter) {
             const uint32_t *hdr = (const uint32_t *)p.motion;
             const uint32_t want = (uint32_t)((nmb * (sizeof(H264B2MbMotion) / 2) + 15) / 16);
-            if (((uintptr_t)hdr & 15) || hdr[0] != H264B2_PACK_MAGIC || hdr[1] != want || hdr[3] < 16 || (hdr[3] & 15)) return fail(-3, "submit: malformed packed motion blob (picture %d)", i);
+            if (!blob_header_ok(hdr, want)) return fail(-3, "submit: malformed packed motion blob (picture %d)", i);
             motion_bytes = hdr[3];
             need += al256((size_t)want * 32) + 256;
             any_packed_m = true;
         }
         if ((p.packed & H264B2_PACKED_COEFS) && p.n_coefs) {
             const uint32_t *hdr = (const uint32_t *)p.coefs;
-            if (((uintptr_t)hdr & 15) || hdr[0] != H264B2_PACK_MAGIC || hdr[1] != (p.n_coefs + 15) / 16 || hdr[3] < 16 || (hdr[3] & 15)) return fail(-3, "submit: malformed packed coefficient blob (picture %d)", i);
+            if (!blob_header_ok(hdr, (p.n_coefs + 15) / 16)) return fail(-3, "submit: malformed packed coefficient blob (picture %d)", i);
             coef_bytes = hdr[3];
             need += al256((size_t)hdr[1] * 32) + 256;      // the dense array k_expand rebuilds
             any_packed = true;
