@@ -820,6 +820,11 @@ static int surf_ptr(H264B2Context *c, int sid, int surface, uint8_t **p) {
 extern "C" int h264b2_surface_ptr(H264B2Context *c, int sid, int surface, void **dev_ptr) {
     uint8_t *p; int r = surf_ptr(c, sid, surface, &p); if (r) return r; *dev_ptr = p; return 0;
 }
+extern "C" int h264b2_debug_intra_tables(int n, uint16_t *out) {
+    if ((n != 4 && n != 8) || !out) return fail(-1, "debug_intra_tables: n must be 4 or 8");
+    fill_intra_tables(n, out);
+    return 0;
+}
 extern "C" int h264b2_set_lookahead(H264B2Context *c, int on) {
     if (!c) return fail(-1, "null context");
     CK(cudaSetDevice(c->device));

@@ -40,6 +40,7 @@ _PROTOS = {
     "h264b2_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "h264b2_sync": (C.c_int, [C.c_void_p]),
     "h264b2_set_lookahead": (C.c_int, [C.c_void_p, C.c_int]),
+    "h264b2_debug_intra_tables": (C.c_int, [C.c_int, C.c_void_p]),
     "h264b2_pack_coefs_bound": (C.c_size_t, [C.c_uint32]),
     "h264b2_pack_coefs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "h264b2_unpack_coefs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),

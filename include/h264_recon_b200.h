@@ -224,6 +224,11 @@ int h264b2_host_free(H264B2Context *ctx, void *host_ptr);
  * on = 0 serialises every kernel on the launch stream (what per-kernel timings and profiles want). */
 int h264b2_set_lookahead(H264B2Context *ctx, int on);
 
+/* Diagnostic (host only, no GPU): the (index, index, index, two-tap) tables the intra kernel uses for the directional modes 3..8 of
+ * Intra_4x4 (n = 4) / Intra_8x8 (n = 8), out[6][n*n]; layout in csrc/intra.cuh (pred_tab_px).  Lets a CPU test hold them against
+ * the prediction equations (H264PictureBase.cpp:1174-1395, 1606-1831). */
+int h264b2_debug_intra_tables(int n, uint16_t *out);
+
 /* Block until all enqueued work is done. */
 int h264b2_sync(H264B2Context *ctx);
 
