@@ -131,39 +131,44 @@ struct Cabac {
     uint32_t range = 0, offset = 0;
     uint8_t state[1024];          // (pStateIdx << 1) | valMPS; 16 bit on purpose: a byte store may alias range / offset / win and would force them through memory after every decision
     void init_contexts(int slice_type, int cabac_init_idc, int slice_qp);
-    // The arithmetic decoder pulls its bits from a 64-bit window that is refilled 32 bits at a time (BitReader::peek is a pure
-    // function of the position, past-the-end behaviour included, so reading ahead changes nothing); br->pos runs `avail` bits
-    // ahead of the decoder and is put back by sync() before anyone else reads the stream (I_PCM samples, re-initialisation).
-    uint64_t win = 0; int avail = 0;
-    inline void sync() { br->pos -= avail; avail = 0; win = 0; }
-    inline uint32_t getbits(int n) {              // n in [0, 32]
-        if (n == 0) return 0;
-        if (avail < n) { win |= (uint64_t)br->peek(32) << (32 - avail); br->pos += 32; avail += 32; }
-        const uint32_t v = (uint32_t)(win >> (64 - n));
-        win <<= n; avail -= n;
-        return v;
-    }
-    void init_engine(BitReader *b) { if (br && avail) sync(); br = b; win = 0; avail = 0; range = 510; offset = br->u(9); }      // re-initialisation inside a slice (I_PCM)
-    void start_slice(BitReader *b) { avail = 0; win = 0; br = b; range = 510; offset = br->u(9); }                            // the window of the previous slice is void
+    // The decoder keeps codIOffset together with the next `k` bits of the stream: V = codIOffset * 2^k + (those k bits), so
+    // "codIOffset < codIRange" is "V < codIRange << k" and a renormalisation shift is just k -= n (no bit is moved).  32 bits are
+    // loaded at a time (BitReader::peek is a pure function of the position, past-the-end behaviour included, so reading ahead
+    // changes nothing); br->pos runs k bits ahead of the reference's read position and is put back by sync() before anyone else
+    // reads the stream (I_PCM samples, re-initialisation).  `offset` is only kept for init / diagnostics.
+    uint64_t V = 0; int k = 0;
+    inline void sync() { br->pos -= k; V >>= k; k = 0; }
+    inline void refill() { V = (V << 32) | br->peek(32); br->pos += 32; k += 32; }
+    void init_engine(BitReader *b) { if (br && k) sync(); br = b; range = 510; offset = br->u(9); V = offset; k = 0; }      // re-initialisation inside a slice (I_PCM)
+    void start_slice(BitReader *b) { br = b; range = 510; offset = br->u(9); V = offset; k = 0; }                          // the look-ahead of the previous slice is void
     inline int decision(int ctx) {
         const uint32_t s = state[ctx];
         const uint32_t rlps = g_range_lps[s >> 1][(range >> 6) & 3];
         range -= rlps;
-        if (offset < range) {
+        const uint64_t scaled = (uint64_t)range << k;
+        if (V < scaled) {
             state[ctx] = g_next_state[0][s];
-            if (range < 256) { range <<= 1; offset = (offset << 1) | getbits(1); }      // the MPS path needs at most one shift
+            if (range < 256) { range <<= 1; if (k == 0) refill(); k--; }      // the MPS path needs at most one shift
             return (int)(s & 1);
         }
-        offset -= range; range = rlps;
+        V -= scaled; range = rlps;
         state[ctx] = g_next_state[1][s];
-        const int n = __builtin_clz(range) - 23; range <<= n; offset = (offset << n) | getbits(n);
+        const int n = __builtin_clz(range) - 23; range <<= n;
+        if (k < n) refill();
+        k -= n;
         return (int)((s & 1) ^ 1);
     }
-    inline int bypass() { offset = (offset << 1) | getbits(1); if (offset >= range) { offset -= range; return 1; } return 0; }
+    inline int bypass() {
+        if (k == 0) refill();
+        k--;
+        const uint64_t scaled = (uint64_t)range << k;
+        if (V >= scaled) { V -= scaled; return 1; }
+        return 0;
+    }
     inline int terminate() {
         range -= 2;
-        if (offset >= range) return 1;
-        if (range < 256) { int n = __builtin_clz(range) - 23; range <<= n; offset = (offset << n) | getbits(n); }
+        if (V >= ((uint64_t)range << k)) return 1;
+        if (range < 256) { const int n = __builtin_clz(range) - 23; range <<= n; if (k < n) refill(); k -= n; }
         return 0;
     }
 };
