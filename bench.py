@@ -414,6 +414,7 @@ def main():
                 "share_of_step": round(dom_ms / ms_serial, 3), "kernels": kernels,
                 "timing": "CUDA events around every launch on its stream, one extra step with the look-ahead stream off (kernels serialised): %.1f ms; the timed steps overlap k_residual/k_bs of batch i+1 with the wavefront kernels of batch i: %.1f ms per step" % (ms_serial, ms / args.steps)}
     kernels["residual"] = {"ms_per_step": round(kt["residual"]["ms"] / kt_steps, 3), "launches_per_step": kt["residual"]["launches"] // kt_steps}
+    kernels["deblock"]["of_which_bs_ms"] = round(kt["bs"]["ms"] / kt_steps, 3)
     launches = sum(kt[k]["launches"] for k in ("residual", "inter", "intra", "bs", "deblock")) * args.steps
 
     # ---- e2e: host buffers in, host pictures out, through the C ABI

@@ -27,6 +27,7 @@
 #include "inter_quad.cuh"
 #include "intra.cuh"
 #include "deblock.cuh"
+#include "deblock_simd.cuh"
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, ...) {
@@ -211,6 +212,7 @@ struct H264B2Context {
     uint8_t *bgr; size_t bgr_cap;             // BGR24 output staging
     // look-ahead (H264B2_LOOKAHEAD, default on): descriptors, unpacking, k_residual and k_bs of batch i+1 need nothing from batch i,
     // so they run on st_pre while the dependency-bound wavefront kernels of batch i leave issue slots idle; res / bs are double-buffered
+    int deblock_v1;                           // H264B2_DEBLOCK_V1=1: first-generation progressive deblocking kernels (A/B runs)
     int lookahead; unsigned batch_no; cudaStream_t st_pre; cudaEvent_t pre_done[DESC_RING], main_done[2];
     size_t bs_stride;                         // words per stream in bs
     // timing
@@ -352,6 +354,7 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     // writes the records with 16-byte stores (an odd macroblock count would misalign every second stream otherwise)
     c->bs_stride = ((size_t)c->nmb * 65 + 3) & ~(size_t)3;
     { const char *e = getenv("H264B2_LOOKAHEAD"); c->lookahead = !(e && atoi(e) == 0); }
+    { const char *e = getenv("H264B2_DEBLOCK_V1"); c->deblock_v1 = e && atoi(e) != 0; }
     CK(cudaMalloc(&c->bs, (size_t)n_streams * c->bs_stride * 4 * 2));
     CK(cudaMalloc(&c->res, (size_t)n_streams * c->nmb * RES_MB_STRIDE * 2 * 2));
     CK(cudaStreamCreateWithFlags(&c->st_pre, cudaStreamNonBlocking));
@@ -523,7 +526,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         class_end(c, 5, sp);
         if (any_deblock) {
             class_begin(c, 3, sp);
-            if (n_prog) k_bs_prog<<<dim3((c->wmb + 7) / 8, c->hmb, n_prog), 256, 0, sp>>>(dd);
+            if (n_prog) { if (c->deblock_v1) k_bs_prog<<<dim3((c->wmb + 7) / 8, c->hmb, n_prog), 256, 0, sp>>>(dd); else k_bs_prog2<<<dim3((c->nmb + 127) / 128, n_prog), 128, 0, sp>>>(dd); }
             if (n - n_prog) k_bs<<<dim3((c->nmb + 7) / 8, n - n_prog), 256, 0, sp>>>(dd + n_prog);
             class_end(c, 3, sp);
         }
@@ -557,7 +560,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         // intra -> deblock chains of the progressive and of the generic (MBAFF) pictures can run side by side
         if (g_deblock && !la) {
             class_begin(c, 3, sg);
-            if (np) k_bs_prog<<<dim3((c->wmb + 7) / 8, c->hmb, np), 256, 0, sg>>>(dg);              // progressive pictures come first in dg
+            if (np) { if (c->deblock_v1) k_bs_prog<<<dim3((c->wmb + 7) / 8, c->hmb, np), 256, 0, sg>>>(dg); else k_bs_prog2<<<dim3((c->nmb + 127) / 128, np), 128, 0, sg>>>(dg); }      // progressive pictures come first in dg
             if (nq) k_bs<<<dim3((c->nmb + 7) / 8, nq), 256, 0, sg>>>(dg + np);
             class_end(c, 3, sg);
         }
@@ -573,7 +576,8 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
             class_end(c, 2, sg);
             if (g_deblock) {
                 class_begin(c, 4, sg);
-                k_deblock<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g + 2);
+                if (c->deblock_v1) k_deblock<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g + 2);
+                else k_deblock2<<<((np + DB_PPW - 1) / DB_PPW) * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g + 2);
                 class_end(c, 4, sg);
             }
         }
@@ -764,12 +768,15 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
     while (i < spans.size()) {
         size_t j = i;
         const uint8_t *lo = spans[i].p; const uint8_t *hi = lo + spans[i].n;
-        while (j + 1 < spans.size() && spans[j + 1].p >= hi && (size_t)(spans[j + 1].p - hi) <= 64) { j++; hi = spans[j].p + spans[j].n; }
+        // the kernels use 16-byte loads on these arrays (header: alignment contract).  A host array that does not start on a 16-byte
+        // boundary (e.g. a numpy view into a file image) travels alone and lands on a 256-byte boundary of the arena instead.
+        const bool lo_ok = ((uintptr_t)lo & 15) == 0;
+        while (lo_ok && j + 1 < spans.size() && spans[j + 1].p >= hi && (size_t)(spans[j + 1].p - hi) <= 64 && ((uintptr_t)spans[j + 1].p & 15) == 0) { j++; hi = spans[j].p + spans[j].n; }
         // keep the host address's offset within 256 so that every array keeps its natural alignment
-        off = al256(off) + ((size_t)(uintptr_t)lo & 255);
+        off = al256(off) + (lo_ok ? ((size_t)(uintptr_t)lo & 255) : 0);
         // picture-sized DMAs leave gaps on one copy queue (profiles/r01_pcie_probe.txt): alternate between two
         cudaPointerAttributes at;
-        if (zc && cudaPointerGetAttributes(&at, lo) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        if (zc && lo_ok && cudaPointerGetAttributes(&at, lo) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
             pull[npull].src = (const uint8_t *)at.devicePointer; pull[npull].dst = c->arena[slot] + off; pull[npull].bytes = (size_t)(hi - lo); npull++;
         } else {
             if (zc) cudaGetLastError();
