@@ -211,8 +211,17 @@ __global__ void __launch_bounds__(128) k_bs_prog2(const PicDev *pics) {
 }
 
 // ------------------------------------------------------------------ the filter kernel
-struct DbTile2 {
-    uint4 blk[DB_PPW][25];            // per picture: 16 luma 4x4 blocks, 2 planes x 4 chroma blocks (+1: 400-byte stride spreads the banks)
+#define DB3_ROWS 8                       // MB rows (warps) per CTA
+#define DB3_THREADS (DB3_ROWS * 32)
+#define DB3_SLOTS 43                     // 4x4-sample blocks of one macroblock with its neighbours: 5x5 luma + 2 x 3x3 chroma
+
+// Shared tile of one macroblock (per picture, double-buffered so that macroblock x+1 is staged while x is filtered).  A slot
+// is one 4x4-sample block = four row words.  Luma block (br, bc), br/bc = -1 (rows above / columns left) .. 3: slot
+// (br+1)*5 + (bc+1); plane c chroma block (br, bc), -1 .. 1: slot 25 + 9c + (br+1)*3 + (bc+1).  Vertical-edge lanes own a
+// block ROW (they walk bc), horizontal-edge lanes a block COLUMN (they walk br): the hand-over between the phases is the
+// tile itself, no copy.
+struct DbTile3 {
+    uint4 blk[2][DB_PPW][DB3_SLOTS];
     uint32_t work[8];                 // bit x: some picture of the bundle has a non-zero strength in macroblock x of this row
     uint32_t work_pic[DB_PPW][8];
 };
@@ -224,86 +233,75 @@ __device__ __forceinline__ DbKind db_kind(uint32_t alpha, uint32_t beta) {
     k.ka = 0x80008000u - alpha * S16_K1; k.kb = 0x80008000u - beta * S16_K1; k.ka4 = 0x80008000u - ((alpha >> 2) + 2u) * S16_K1;
     return k;
 }
-__device__ __forceinline__ DbPar2 db_par(uint32_t codes, uint32_t sel, const DbKind &kd, uint32_t lum) {
-    const uint32_t pair = s16_prmt(codes, 0u, sel);
-    DbPar2 k;
-    k.kalpha = kd.ka; k.kbeta = kd.kb; k.kalpha4 = kd.ka4; k.tc0 = pair & 0x001F001Fu; k.act = s16_sign(pair << 9); k.s4 = s16_sign(pair << 8); k.lum = lum;
-    return k;
-}
 
-// One phase (vertical edges: VERT, lanes hold 4 rows; horizontal edges: lanes hold 4 columns) of one macroblock: four steps,
-// step s filters the edge between block s-1 (L for s = 0) and block s.  Luma lanes walk L | B0 | B1 | B2 | B3; chroma lanes hold
-// L | B0 | B2 and filter in steps 0 and 2 (their codes for steps 1 and 3 are zero), so that steps 1 and 3 — the edges a
-// transform_size_8x8 macroblock does not have — vanish for the whole warp when no luma lane needs them.
+// One phase of one macroblock: step s filters the edge between the lane's blocks s-1 and s (luma) — chroma lanes have two
+// blocks and filter in steps 0 and 2, so steps 1 and 3 (the edges a transform_size_8x8 macroblock does not have) vanish for
+// the whole warp when no luma lane needs them.  The loop is NOT unrolled: one copy of the filter per phase keeps the kernel
+// inside the instruction cache (the unrolled first version stalled on instruction fetch as much as on data, ncu).
 template <bool VERT>
-__device__ __forceinline__ void db_phase(uint32_t (&L)[4], uint32_t (&B)[4][4], uint32_t codes, const uint32_t (&sel)[4], const DbKind &k0, const DbKind &kI, uint32_t lum) {
-    const bool chroma = lum == 0u;
-    uint32_t Pe[4], Po[4];
-    if (VERT) blk_rows_to_colpairs(L, Pe, Po); else blk_rows_to_rowpairs(L, Pe, Po);
-#pragma unroll
+__device__ __forceinline__ void db3_phase(uint4 *tile, int base, int mul, bool chroma, uint32_t codes, const DbKind &k0, const DbKind &kI, uint32_t lum) {
+#pragma unroll 1
     for (int s = 0; s < 4; s++) {
-        uint32_t Qe[4], Qo[4];
-        if (VERT) blk_rows_to_colpairs(B[s], Qe, Qo); else blk_rows_to_rowpairs(B[s], Qe, Qo);
-        const DbPar2 k = db_par(codes, sel[s], s == 0 ? k0 : kI, lum);
-        if (__any_sync(0xffffffffu, k.act != 0u)) {
-            db_filter2(Pe[0], Pe[1], Pe[2], Pe[3], Qe[0], Qe[1], Qe[2], Qe[3], k);
-            db_filter2(Po[0], Po[1], Po[2], Po[3], Qo[0], Qo[1], Qo[2], Qo[3], k);
-        }
-        uint32_t R[4];
-        if (VERT) blk_colpairs_to_rows(Pe, Po, R); else blk_rowpairs_to_rows(Pe, Po, R);
-        if (s == 0) {
-#pragma unroll
-            for (int t = 0; t < 4; t++) L[t] = R[t];
-        } else if (s == 1) {
-#pragma unroll
-            for (int t = 0; t < 4; t++) B[0][t] = R[t];
-        } else if (s == 2) {
-#pragma unroll
-            for (int t = 0; t < 4; t++) { B[0][t] = chroma ? R[t] : B[0][t]; B[1][t] = chroma ? B[1][t] : R[t]; }
-        } else {
-#pragma unroll
-            for (int t = 0; t < 4; t++) B[2][t] = R[t];
-            if (VERT) blk_colpairs_to_rows(Qe, Qo, B[3]); else blk_rowpairs_to_rows(Qe, Qo, B[3]);
-        }
-        if (s == 1) {
-#pragma unroll
-            for (int t = 0; t < 4; t++) { Pe[t] = chroma ? Pe[t] : Qe[t]; Po[t] = chroma ? Po[t] : Qo[t]; }
-        } else {
-#pragma unroll
-            for (int t = 0; t < 4; t++) { Pe[t] = Qe[t]; Po[t] = Qo[t]; }
-        }
+        uint32_t pair = s16_prmt(codes, 0u, (chroma ? 0x4140u : 0x4040u) + (uint32_t)s * 0x0101u);
+        if (chroma && (s & 1)) pair = 0u;
+        const uint32_t act = s16_sign(pair << 9), s4 = s16_sign(pair << 8);
+        const bool do3 = __any_sync(0xffffffffu, (act & ~s4) != 0u), do4 = __any_sync(0xffffffffu, s4 != 0u);
+        if (!(do3 || do4)) continue;
+        DbPar2 k;
+        k.kalpha = s == 0 ? k0.ka : kI.ka; k.kbeta = s == 0 ? k0.kb : kI.kb; k.kalpha4 = s == 0 ? k0.ka4 : kI.ka4;
+        k.tc0 = pair & 0x001F001Fu; k.act = act; k.s4 = s4; k.lum = lum;
+        const int ps = base + mul * (chroma ? (s >> 1) : s), qs = ps + mul;
+        const uint4 pv = tile[ps], qv = tile[qs];
+        uint32_t P[4] = { pv.x, pv.y, pv.z, pv.w }, Q[4] = { qv.x, qv.y, qv.z, qv.w };
+        uint32_t Pe[4], Po[4], Qe[4], Qo[4];
+        if (VERT) { blk_rows_to_colpairs(P, Pe, Po); blk_rows_to_colpairs(Q, Qe, Qo); }
+        else { blk_rows_to_rowpairs(P, Pe, Po); blk_rows_to_rowpairs(Q, Qe, Qo); }
+        db_filter2(Pe[0], Pe[1], Pe[2], Pe[3], Qe[0], Qe[1], Qe[2], Qe[3], k, do3, do4);
+        db_filter2(Po[0], Po[1], Po[2], Po[3], Qo[0], Qo[1], Qo[2], Qo[3], k, do3, do4);
+        if (VERT) { blk_colpairs_to_rows(Pe, Po, P); blk_colpairs_to_rows(Qe, Qo, Q); }
+        else { blk_rowpairs_to_rows(Pe, Po, P); blk_rowpairs_to_rows(Qe, Qo, Q); }
+        tile[ps] = make_uint4(P[0], P[1], P[2], P[3]);
+        tile[qs] = make_uint4(Q[0], Q[1], Q[2], Q[3]);
     }
 }
 
-struct DbFetch { uint32_t B[4][4], Lg[4]; uint2 codes, thr; };
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(g) : "memory"); }
 
-// grid: CTAs draw (band, bundle) tickets; block: WF_ROWS warps = WF_ROWS consecutive MB rows of one bundle of DB_PPW pictures
-__global__ void __launch_bounds__(WF_THREADS, 1) k_deblock2(const PicDev *pics, int npics, int bands, int *ticket) {
-    __shared__ DbTile2 tiles[WF_ROWS];
-    __shared__ int s_prog[WF_ROWS];
-    __shared__ uint64_t s_bar[WF_ROWS];
+#ifdef DB3_CLOCKS
+#define DB3_T(i) do { const long long t_ = clock64(); sec[i] += t_ - tlast; tlast = t_; } while (0)
+#else
+#define DB3_T(i) do { } while (0)
+#endif
+// grid: CTAs draw (band, bundle) tickets; block: DB3_ROWS warps = consecutive MB rows of one bundle of DB_PPW pictures
+#ifndef DB3_MIN_CTAS
+#define DB3_MIN_CTAS 3                   // 80 registers: the 64-register build spills inside the filter loop and is 25 % slower (measured)
+#endif
+__global__ void __launch_bounds__(DB3_THREADS, DB3_MIN_CTAS) k_deblock3(const PicDev *pics, int npics, int bands, int *ticket) {
+    __shared__ DbTile3 tiles[DB3_ROWS];
+    __shared__ int s_prog[DB3_ROWS];
+    __shared__ uint64_t s_bar[DB3_ROWS];
     __shared__ int s_ticket;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
-    if (threadIdx.x < WF_ROWS) { s_prog[threadIdx.x] = 0; mbar_init(&s_bar[threadIdx.x], 1); }
+    if (threadIdx.x < DB3_ROWS) { s_prog[threadIdx.x] = 0; mbar_init(&s_bar[threadIdx.x], 1); }
     __syncthreads();
     const int nbundles = (npics + DB_PPW - 1) / DB_PPW;
     const int tk = s_ticket;
     if (tk >= nbundles * bands) return;
     const int bundle = tk % nbundles;
-    const int row = (tk / nbundles) * WF_ROWS + warp;
+    const int row = (tk / nbundles) * DB3_ROWS + warp;
     const PicDev &P0 = pics[bundle * DB_PPW];
     const int wmb = P0.wmb, hmb = P0.hmb, nmb = wmb * hmb;
     if (row >= hmb) return;
     const int W = wmb * 16, H = hmb * 16, Wc = W >> 1;
-    DbTile2 &T = tiles[warp];
-    RowSync rs = rs_init(s_prog, s_bar, warp, row, hmb, P0.progress + hmb, wmb);      // the bundle advances on its first picture's counters
+    DbTile3 &T = tiles[warp];
+    RowSync rs = rs_init(s_prog, s_bar, warp, row, hmb, P0.progress + hmb, wmb, DB3_ROWS);      // the bundle advances on its first picture's counters
 
     // ---- work bitmaps of this row
     for (int p = 0; p < DB_PPW; p++) {
         const int pi = bundle * DB_PPW + p;
-        const bool pv = pi < npics && pics[min(pi, npics - 1)].deblock_enable;
         const PicDev &Pp = pics[min(pi, npics - 1)];
+        const bool pv = pi < npics && Pp.deblock_enable;
         for (int g = 0; g < 8; g++) {
             const int xl = g * 32 + lane;
             int wk = 0;
@@ -328,55 +326,48 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_deblock2(const PicDev *pics, 
     uint8_t *hcol = plane + (size_t)(row * mbw - 4) * rstride + 4 * (chroma ? hw : sub);
     const uint32_t *recs = P.bs + (size_t)row * wmb * DBREC_WORDS + 2 * sub;
     const uint32_t *thrs = P.bs + (size_t)row * wmb * DBREC_WORDS + 16 + 2 * (chroma ? 1 + cpl : 0);
-    uint32_t sel[4];
-    sel[0] = chroma ? 0x4140u : 0x4040u; sel[1] = chroma ? 0x4444u : 0x4141u; sel[2] = chroma ? 0x4342u : 0x4242u; sel[3] = chroma ? 0x4444u : 0x4343u;
-    // tile slots: vertical-phase lane (block row i) writes block (i, s) at slot 4i + (s ^ i); horizontal-phase lane (block column j)
-    // reads block (s, j) at slot 4s + (j ^ s).  Chroma plane c: slot 16 + 4c + 2*half + word.
-    uint4 *tile = T.blk[pic];
-    int wr[4], rd[4];
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-        wr[s] = chroma ? 16 + 4 * cpl + 2 * hw + (s >> 1) : 4 * sub + (s ^ sub);
-        rd[s] = chroma ? 16 + 4 * cpl + 2 * (s >> 1) + hw : 4 * s + (sub ^ s);
-    }
+    const int vbase = chroma ? 25 + 9 * cpl + (hw + 1) * 3 : (sub + 1) * 5;     // this lane's block row: slots vbase .. vbase+4 (chroma +2)
+    const int hbase = chroma ? 25 + 9 * cpl + hw + 1 : sub + 1;                  // this lane's block column: slots hbase + k*hmul
+    const int hmul = chroma ? 3 : 5;
 
-    auto fetch = [&](int x, bool need_left, DbFetch &f) {
-        const uint8_t *r0 = vrow + (size_t)x * mbw;
+    // Prefetch of macroblock x into tile buffer b: the samples go straight from global to shared memory (cp.async, 4 bytes per
+    // (row, word): the tile is block-major), so no register carries them across the filtering of the current macroblock; the two
+    // record words travel in registers.  Own rows and the columns left of them are not written by any other warp before this
+    // warp filters them, so the L1-allocating form is safe.
+    auto fetch = [&](int x, bool need_left, int b, uint2 &codes, uint2 &thr) {
+        codes = make_uint2(0u, 0u); thr = make_uint2(0u, 0u);
         if (valid) {
-            if (!chroma) {
+            const uint8_t *r0 = vrow + (size_t)x * mbw;
+            const uint32_t dst = smem_addr(&T.blk[b][pic][vbase]);
 #pragma unroll
-                for (int t = 0; t < 4; t++) { const uint4 v = __ldcg((const uint4 *)(r0 + (size_t)t * rstride)); f.B[0][t] = v.x; f.B[1][t] = v.y; f.B[2][t] = v.z; f.B[3][t] = v.w; }
-            } else {
-#pragma unroll
-                for (int t = 0; t < 4; t++) { const uint2 v = __ldcg((const uint2 *)(r0 + (size_t)t * rstride)); f.B[0][t] = v.x; f.B[2][t] = v.y; f.B[1][t] = 0; f.B[3][t] = 0; }
-            }
-            if (need_left && x > 0) {
-#pragma unroll
-                for (int t = 0; t < 4; t++) f.Lg[t] = ldcg32(r0 + (size_t)t * rstride - 4);
+            for (int t = 0; t < 4; t++) {
+                const uint8_t *rp = r0 + (size_t)t * rstride;
+                cp_async4(dst + 16 + 4 * t, rp); cp_async4(dst + 32 + 4 * t, rp + 4);
+                if (!chroma) { cp_async4(dst + 48 + 4 * t, rp + 8); cp_async4(dst + 64 + 4 * t, rp + 12); }
+                if (need_left && x > 0) cp_async4(dst + 4 * t, rp - 4);
             }
             const bool wk = (T.work_pic[pic][x >> 5] >> (x & 31)) & 1u;
-            f.codes = make_uint2(0u, 0u); f.thr = make_uint2(0u, 0u);
-            if (wk) { f.codes = *(const uint2 *)(recs + (size_t)x * DBREC_WORDS); f.thr = *(const uint2 *)(thrs + (size_t)x * DBREC_WORDS); }
+            if (wk) { codes = *(const uint2 *)(recs + (size_t)x * DBREC_WORDS); thr = *(const uint2 *)(thrs + (size_t)x * DBREC_WORDS); }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+#ifdef DB3_CLOCKS
+    long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(); int iters = 0;
+#endif
     int x = db_next_work(T.work, -1, wmb);
-    bool carry = false;
-    DbFetch cur, nxt;
-#pragma unroll
-    for (int s = 0; s < 4; s++)
-#pragma unroll
-        for (int t = 0; t < 4; t++) { cur.B[s][t] = 0; nxt.B[s][t] = 0; }
-#pragma unroll
-    for (int t = 0; t < 4; t++) { cur.Lg[t] = 0; nxt.Lg[t] = 0; }
-    cur.codes = nxt.codes = make_uint2(0u, 0u); cur.thr = nxt.thr = make_uint2(0u, 0u);
-    uint32_t Lc[4] = {0, 0, 0, 0};                                          // right-hand block of the previous macroblock (carried in registers)
-    if (x < wmb) fetch(x, true, cur);
+    int buf = 0;
+    uint2 codes = make_uint2(0u, 0u), thr = make_uint2(0u, 0u), ncodes = codes, nthr = thr;
+    if (x < wmb) fetch(x, true, 0, codes, thr);
     while (x < wmb) {
+        uint4 *tile = T.blk[buf][pic];
         const int xn = db_next_work(T.work, x, wmb);
-        if (xn < wmb) fetch(xn, xn != x + 1, nxt);
-        const DbKind kL = db_kind(cur.thr.x & 0xffu, (cur.thr.x >> 8) & 0xffu), kT = db_kind((cur.thr.x >> 16) & 0xffu, cur.thr.x >> 24), kI = db_kind(cur.thr.y & 0xffu, (cur.thr.y >> 8) & 0xffu);
-        const int topf = __any_sync(0xffffffffu, (s16_prmt(cur.codes.y, 0u, sel[0]) & 0x00400040u) != 0u);
+        const bool carry = xn == x + 1;
+        DB3_T(7);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");              // macroblock x has landed in tile[buf] (this lane's own copies)
+        DB3_T(0);
+        if (xn < wmb) fetch(xn, !carry, buf ^ 1, ncodes, nthr);
+        const int topf = __any_sync(0xffffffffu, (s16_prmt(codes.y, 0u, chroma ? 0x4140u : 0x4040u) & 0x00400040u) != 0u);
         // rows above: fetch them early when the row above is already far enough, so that their latency hides behind the vertical phase
         uint32_t Ab[4] = {0, 0, 0, 0};
         const uint8_t *ap = hcol + (size_t)x * mbw;
@@ -385,68 +376,72 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_deblock2(const PicDev *pics, 
 #pragma unroll
             for (int t = 0; t < 4; t++) Ab[t] = ldcg32(ap + (size_t)t * rstride);
         }
-        // ---- vertical edges
-        uint32_t L[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) L[t] = carry ? Lc[t] : cur.Lg[t];
-        db_phase<true>(L, cur.B, cur.codes.x, sel, kL, kI, lum);
-        if (valid && x > 0) {
-            uint8_t *r0 = vrow + (size_t)x * mbw - 4;
-#pragma unroll
-            for (int t = 0; t < 4; t++) *(uint32_t *)(r0 + (size_t)t * rstride) = L[t];
+        const DbKind kI = db_kind(thr.y & 0xffu, (thr.y >> 8) & 0xffu);
+        DB3_T(1);
+        // ---- vertical edges (lanes own block rows)
+        {
+            const DbKind kL = db_kind(thr.x & 0xffu, (thr.x >> 8) & 0xffu);
+            db3_phase<true>(tile, vbase, 1, chroma, codes.x, kL, kI, lum);
         }
+        DB3_T(2);
+        if (topf) {
+            if (!early) {
+                rs_wait(rs, min(x + 2, wmb), x, lane);
+                if (valid) {
 #pragma unroll
-        for (int s = 0; s < 4; s++) if (!chroma || !(s & 1)) tile[wr[s]] = make_uint4(cur.B[s][0], cur.B[s][1], cur.B[s][2], cur.B[s][3]);
-        if (topf && !early) {
-            rs_wait(rs, min(x + 2, wmb), x, lane);
-            if (valid) {
-#pragma unroll
-                for (int t = 0; t < 4; t++) Ab[t] = ldcg32(ap + (size_t)t * rstride);
+                    for (int t = 0; t < 4; t++) Ab[t] = ldcg32(ap + (size_t)t * rstride);
+                }
             }
+            tile[hbase] = make_uint4(Ab[0], Ab[1], Ab[2], Ab[3]);
         }
         __syncwarp();
-        // ---- horizontal edges
-        uint32_t HB[4][4];
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (!chroma || !(s & 1)) v = tile[rd[s]];
-            HB[s][0] = v.x; HB[s][1] = v.y; HB[s][2] = v.z; HB[s][3] = v.w;
+        DB3_T(3);
+        // ---- horizontal edges (lanes own block columns)
+        {
+            const DbKind kT = db_kind((thr.x >> 16) & 0xffu, thr.x >> 24);
+            db3_phase<false>(tile, hbase, hmul, chroma, codes.y, kT, kI, lum);
         }
-        db_phase<false>(Ab, HB, cur.codes.y, sel, kT, kI, lum);
+        DB3_T(4);
         if (topf && valid) {
+            const uint4 a = tile[hbase];
             uint8_t *o = hcol + (size_t)x * mbw;
-#pragma unroll
-            for (int t = 1; t < 4; t++) *(uint32_t *)(o + (size_t)t * rstride) = Ab[t];
+            *(uint32_t *)(o + (size_t)rstride) = a.y; *(uint32_t *)(o + (size_t)2 * rstride) = a.z; *(uint32_t *)(o + (size_t)3 * rstride) = a.w;
         }
-        __syncwarp();                                                       // every lane has read its blocks: the slots can be overwritten
-#pragma unroll
-        for (int s = 0; s < 4; s++) if (!chroma || !(s & 1)) tile[rd[s]] = make_uint4(HB[s][0], HB[s][1], HB[s][2], HB[s][3]);
         __syncwarp();
-        // ---- final rows of this macroblock, back in the row layout
-        uint32_t F[4][4];
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (!chroma || !(s & 1)) v = tile[wr[s]];
-            F[s][0] = v.x; F[s][1] = v.y; F[s][2] = v.z; F[s][3] = v.w;
-        }
-        if (valid) {
+        // ---- final rows of this macroblock (row layout again), the finished columns left of it, the carry into the next macroblock
+        {
             uint8_t *r0 = vrow + (size_t)x * mbw;
+            const uint4 b0 = tile[vbase + 1], b1 = tile[vbase + 2];
+            uint4 last = b1;
             if (!chroma) {
-#pragma unroll
-                for (int t = 0; t < 4; t++) *(uint4 *)(r0 + (size_t)t * rstride) = make_uint4(F[0][t], F[1][t], F[2][t], F[3][t]);
-            } else {
-#pragma unroll
-                for (int t = 0; t < 4; t++) *(uint2 *)(r0 + (size_t)t * rstride) = make_uint2(F[0][t], F[2][t]);
+                const uint4 b2 = tile[vbase + 3], b3 = tile[vbase + 4];
+                last = b3;
+                if (valid) {
+                    *(uint4 *)(r0) = make_uint4(b0.x, b1.x, b2.x, b3.x); *(uint4 *)(r0 + (size_t)rstride) = make_uint4(b0.y, b1.y, b2.y, b3.y);
+                    *(uint4 *)(r0 + (size_t)2 * rstride) = make_uint4(b0.z, b1.z, b2.z, b3.z); *(uint4 *)(r0 + (size_t)3 * rstride) = make_uint4(b0.w, b1.w, b2.w, b3.w);
+                }
+            } else if (valid) {
+                *(uint2 *)(r0) = make_uint2(b0.x, b1.x); *(uint2 *)(r0 + (size_t)rstride) = make_uint2(b0.y, b1.y);
+                *(uint2 *)(r0 + (size_t)2 * rstride) = make_uint2(b0.z, b1.z); *(uint2 *)(r0 + (size_t)3 * rstride) = make_uint2(b0.w, b1.w);
             }
+            if (valid && x > 0) {
+                const uint4 l = tile[vbase];
+                *(uint32_t *)(r0 - 4) = l.x; *(uint32_t *)(r0 + (size_t)rstride - 4) = l.y; *(uint32_t *)(r0 + (size_t)2 * rstride - 4) = l.z; *(uint32_t *)(r0 + (size_t)3 * rstride - 4) = l.w;
+            }
+            if (carry) T.blk[buf ^ 1][pic][vbase] = last;
         }
-#pragma unroll
-        for (int t = 0; t < 4; t++) Lc[t] = chroma ? F[2][t] : F[3][t];
-        carry = xn == x + 1;
+        codes = ncodes; thr = nthr;
+        DB3_T(5);
         rs_publish(rs, carry ? x + 1 : min(xn, wmb), lane);      // no work up to xn: those columns are final as they are
+        DB3_T(6);
+#ifdef DB3_CLOCKS
+        iters++;
+#endif
+        buf ^= 1;
         x = xn;
-        cur = nxt;
     }
+#ifdef DB3_CLOCKS
+    if (lane == 0 && bundle == 0 && (row == 20 || row == 23 || row == 24)) printf("DB3CLK row %d iters %d: cpwait %lld fetch+top %lld V %lld topwait %lld H %lld final %lld publish %lld loop %lld\n", row, iters, sec[0] / iters, sec[1] / iters, sec[2] / iters, sec[3] / iters, sec[4] / iters, sec[5] / iters, sec[6] / iters, sec[7] / iters);
+#endif
     rs_publish(rs, wmb, lane);
 }

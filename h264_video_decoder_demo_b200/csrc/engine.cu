@@ -577,7 +577,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
             if (g_deblock) {
                 class_begin(c, 4, sg);
                 if (c->deblock_v1) k_deblock<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g + 2);
-                else k_deblock2<<<((np + DB_PPW - 1) / DB_PPW) * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g + 2);
+                else { const int bands3 = (c->hmb + DB3_ROWS - 1) / DB3_ROWS; k_deblock3<<<((np + DB_PPW - 1) / DB_PPW) * bands3, DB3_THREADS, 0, sg>>>(dg, np, bands3, tickets + 4 * g + 2); }
                 class_end(c, 4, sg);
             }
         }

@@ -51,18 +51,18 @@ S16_FN uint32_t s16_ge_k(uint32_t thr) { return (0x8000u - thr) * S16_K1; }
 // lum: all ones for luma lines, 0 for chroma lines (chromaStyleFilteringFlag, DB:959).
 struct DbPar2 { uint32_t kalpha, kbeta, kalpha4, tc0, act, s4, lum; };
 
-// DB:1373-1478 (bS < 4) and DB:1481-1522 (bS == 4) for two sample lines at once.
-S16_FN void db_filter2(uint32_t &P3, uint32_t &P2, uint32_t &P1, uint32_t &P0, uint32_t &Q0, uint32_t &Q1, uint32_t &Q2, uint32_t &Q3, const DbPar2 &k) {
+// DB:1373-1478 (bS < 4) and DB:1481-1522 (bS == 4) for two sample lines at once.  No data-dependent branch: do3 / do4 say whether
+// any line of the CALLER'S WARP has 0 < bS < 4 / bS == 4 (warp-uniform, from the step codes alone), so the only branches are uniform.
+S16_FN void db_filter2(uint32_t &P3, uint32_t &P2, uint32_t &P1, uint32_t &P0, uint32_t &Q0, uint32_t &Q1, uint32_t &Q2, uint32_t &Q3, const DbPar2 &k, bool do3, bool do4) {
     const uint32_t dpq = s16_absdiff(P0, Q0);
     const uint32_t ge_a = s16_sign(dpq + k.kalpha);
     const uint32_t ge_b = s16_sign(s16_maxu(s16_absdiff(P1, P0), s16_absdiff(Q1, Q0)) + k.kbeta);
     const uint32_t cond = k.act & ~(ge_a | ge_b);                                      // filterSamplesFlag (DB:1366) of lines with bS > 0
-    if (cond == 0u) return;
     const uint32_t apm = ~s16_sign(s16_absdiff(P2, P0) + k.kbeta) & k.lum;             // ap < beta, luma only
     const uint32_t aqm = ~s16_sign(s16_absdiff(Q2, Q0) + k.kbeta) & k.lum;
     const uint32_t m3 = cond & ~k.s4, m4 = cond & k.s4;
     uint32_t nP0 = P0, nP1 = P1, nP2 = P2, nQ0 = Q0, nQ1 = Q1, nQ2 = Q2;
-    if (m3) {
+    if (do3) {
         const uint32_t tc = k.tc0 + (apm & S16_K1) + (aqm & S16_K1) + (~k.lum & S16_K1);
         // ((q0 - p0) * 4 + (p1 - q1) + 4) + 2048 with every term non-negative; >> 3 gives delta + 256
         const uint32_t t = ((Q0 + (P0 ^ S16_KFF)) << 2) + P1 + (Q1 ^ S16_KFF) + 777u * S16_K1;
@@ -81,7 +81,7 @@ S16_FN void db_filter2(uint32_t &P3, uint32_t &P2, uint32_t &P1, uint32_t &P0, u
         nP0 = s16_sel(m3, a0, nP0); nQ0 = s16_sel(m3, b0, nQ0);
         nP1 = s16_sel(m3 & apm, a1, nP1); nQ1 = s16_sel(m3 & aqm, b1, nQ1);
     }
-    if (m4) {
+    if (do4) {
         const uint32_t small = ~s16_sign(dpq + k.kalpha4);                             // |p0 - q0| < (alpha >> 2) + 2
         const uint32_t ps = m4 & apm & small, qs = m4 & aqm & small;
         const uint32_t S = P0 + Q0, Tp = P1 + S, Tq = Q1 + S;

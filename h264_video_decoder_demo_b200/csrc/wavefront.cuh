@@ -33,6 +33,9 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v) {
 // of polling the shared counter — ncu showed two thirds of k_intra's executed instructions in the nanosleep poll loop.  The
 // counter stays the source of truth: the waiter re-reads it after every wake-up (mbarrier.try_wait also returns after a
 // hardware time limit, so a stale phase guess costs a delay, never a hang).
+#ifndef WF_PARK_NS
+#define WF_PARK_NS 0
+#endif
 #ifndef WF_MBAR
 #define WF_MBAR 1
 #endif
@@ -45,57 +48,75 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ int mbar_try_wait(uint32_t bar, int parity) {
     int ok;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.s32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    // optional suspend-time hint (WF_PARK_NS > 0).  Measured on B200 (round 2): without a hint the wait comes back after ~70 ns whether
+    // or not the phase completed, so the loop around it polls; with a 20 us hint the warp really parks, but wakes up so late after the
+    // arrival that the wavefront's critical path grew by 30 % (single-bundle latency 84 -> 108 ms per 75 pictures).  Default: no hint.
+    if (WF_PARK_NS > 0)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.s32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity), "r"(WF_PARK_NS) : "memory");
+    else
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.s32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
 
 struct RowSync {
     uint32_t bar_above, bar_mine;   // mbarriers (shared addresses) of the row above / of this row
-    int phase;                      // completed phases of bar_above this warp has consumed (its parity is what matters)
-    volatile int *s_above;   // shared counter of the row above (same band), or nullptr
-    volatile int *s_mine;    // shared counter of this row
+    int gen;                        // arrivals this row has made on bar_mine so far
+    volatile int *s_above;   // shared progress word of the row above (same band), or nullptr
+    volatile int *s_mine;    // shared progress word of this row: (announced arrivals << 16) | progress
     int *g_above;            // global counter of the row above (other band), or nullptr when this is row 0
     int *g_mine;             // global counter of this row, or nullptr when no other band reads it
     int seen;                // last observed progress of the row above
     int width;
 };
 
-__device__ __forceinline__ RowSync rs_init(int *s_prog, uint64_t *s_bar, int warp, int row, int rows, int *g_prog, int width) {
+__device__ __forceinline__ RowSync rs_init(int *s_prog, uint64_t *s_bar, int warp, int row, int rows, int *g_prog, int width, int band_rows = WF_ROWS) {
     RowSync r;
-    r.bar_mine = smem_addr(s_bar + warp); r.bar_above = warp > 0 ? smem_addr(s_bar + warp - 1) : 0; r.phase = 0;
+    r.bar_mine = smem_addr(s_bar + warp); r.bar_above = warp > 0 ? smem_addr(s_bar + warp - 1) : 0; r.gen = 0;
     r.s_mine = s_prog + warp;
     r.s_above = warp > 0 ? s_prog + warp - 1 : nullptr;
     r.g_above = (warp == 0 && row > 0) ? g_prog + row - 1 : nullptr;
-    r.g_mine = (warp == WF_ROWS - 1 && row + 1 < rows) ? g_prog + row : nullptr;
+    r.g_mine = (warp == band_rows - 1 && row + 1 < rows) ? g_prog + row : nullptr;
     r.seen = row == 0 ? width : 0;
     r.width = width;
     return r;
+}
+
+// Shared hand-over protocol (lane 0 of the publishing row): write (gen + 1) << 16 | progress, THEN arrive (which completes phase
+// number gen of the row's mbarrier).  A waiter that reads (g, s) with s too small parks on phase g: if arrival g - 1 has been
+// announced but not yet performed, the wait returns at once and the word is read again; once phase g is current the warp
+// sleeps in hardware until the next publish.  No wake-up can be lost and the waiter keeps no count of its own.
+__device__ __forceinline__ void rs_store_mine(RowSync &r, int v) {
+    r.gen++;
+    *r.s_mine = (r.gen << 16) | v;
+    if (WF_MBAR) mbar_arrive(r.bar_mine);
+    if (r.g_mine) st_release_gpu(r.g_mine, v);
 }
 
 // publish "columns < v of this row are final".  Call with the whole warp converged.
 __device__ __forceinline__ void rs_publish(RowSync &r, int v, int lane) {
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) {
-        *r.s_mine = v;
-        if (WF_MBAR) mbar_arrive(r.bar_mine);
-        if (r.g_mine) st_release_gpu(r.g_mine, v);
-    }
+    if (lane == 0) rs_store_mine(r, v);
 }
 
 // block until the row above has published >= need; `mine` = what this row can publish meanwhile
 __device__ __forceinline__ void rs_wait(RowSync &r, int need, int mine, int lane) {
     if (r.seen >= need) return;
     if (lane == 0) {
-        *r.s_mine = mine;                          // nothing of ours is pending: everything left of `mine` was published with a fence
-        if (WF_MBAR) mbar_arrive(r.bar_mine);
-        if (r.g_mine) st_release_gpu(r.g_mine, mine);
+        rs_store_mine(r, mine);                    // nothing of ours is pending: everything left of `mine` was published with a fence
         int s;
         if (r.s_above) {
-            if (WF_MBAR) { while ((s = *r.s_above) < need) r.phase += mbar_try_wait(r.bar_above, r.phase & 1); }
-            else { while ((s = *r.s_above) < need) __nanosleep(WF_POLL_NS); }
+            for (;;) {
+                const int w = *r.s_above;
+                s = w & 0xffff;
+                if (s >= need) break;
+                if (WF_MBAR) mbar_try_wait(r.bar_above, (w >> 16) & 1); else __nanosleep(WF_POLL_NS);
+            }
+        } else {
+            // another band (another CTA): poll the global counter, sleeping longer the further away the row above still is
+            while ((s = ld_relaxed_flag(r.g_above)) < need) __nanosleep(need - s > 2 ? 8 * WF_POLL_NS : WF_POLL_NS);
+            __threadfence();
         }
-        else { while ((s = ld_relaxed_flag(r.g_above)) < need) __nanosleep(2 * WF_POLL_NS); __threadfence(); }
         r.seen = s;
     }
     r.seen = __shfl_sync(0xffffffffu, r.seen, 0);
@@ -107,7 +128,7 @@ __device__ __forceinline__ void rs_wait(RowSync &r, int need, int mine, int lane
 __device__ __forceinline__ bool rs_try(RowSync &r, int need, int lane) {
     if (r.seen >= need) return true;
     int s = 0;
-    if (lane == 0) s = r.s_above ? *r.s_above : ld_relaxed_flag(r.g_above);
+    if (lane == 0) s = r.s_above ? (*r.s_above & 0xffff) : ld_relaxed_flag(r.g_above);
     s = __shfl_sync(0xffffffffu, s, 0);
     if (s < need) return false;
     r.seen = s;

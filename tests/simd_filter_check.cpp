@@ -71,12 +71,16 @@ int main(int argc, char **argv) {
             k[h].s4 = (b0 == 4 ? 0xFFFFu : 0u) | (b1 == 4 ? 0xFFFF0000u : 0u);
             k[h].lum = chroma ? 0u : 0xFFFFFFFFu;
         }
+        // warp-uniform path switches: exact (only the paths some line needs) or both always on
+        const bool exact = rnd() & 1;
+        bool do3 = !exact, do4 = !exact;
+        for (int r = 0; r < 4; r++) { if (bS[r] >= 1 && bS[r] <= 3) do3 = true; if (bS[r] == 4) do4 = true; }
         if (vertical) {
             uint32_t rp[4], rq[4], pe[4], po[4], qe[4], qo[4];
             for (int r = 0; r < 4; r++) { memcpy(&rp[r], &px[r][0], 4); memcpy(&rq[r], &px[r][4], 4); }
             blk_rows_to_colpairs(rp, pe, po); blk_rows_to_colpairs(rq, qe, qo);
-            db_filter2(pe[0], pe[1], pe[2], pe[3], qe[0], qe[1], qe[2], qe[3], k[0]);
-            db_filter2(po[0], po[1], po[2], po[3], qo[0], qo[1], qo[2], qo[3], k[1]);
+            db_filter2(pe[0], pe[1], pe[2], pe[3], qe[0], qe[1], qe[2], qe[3], k[0], do3, do4);
+            db_filter2(po[0], po[1], po[2], po[3], qo[0], qo[1], qo[2], qo[3], k[1], do3, do4);
             blk_colpairs_to_rows(pe, po, rp); blk_colpairs_to_rows(qe, qo, rq);
             for (int r = 0; r < 4; r++) { memcpy(&got[r][0], &rp[r], 4); memcpy(&got[r][4], &rq[r], 4); }
         } else {
@@ -84,8 +88,8 @@ int main(int argc, char **argv) {
             uint32_t rp[4], rq[4], pe[4], po[4], qe[4], qo[4];
             for (int c = 0; c < 4; c++) { rp[c] = rq[c] = 0; for (int r = 0; r < 4; r++) { rp[c] |= (uint32_t)px[r][c] << (8 * r); rq[c] |= (uint32_t)px[r][4 + c] << (8 * r); } }
             blk_rows_to_rowpairs(rp, pe, po); blk_rows_to_rowpairs(rq, qe, qo);
-            db_filter2(pe[0], pe[1], pe[2], pe[3], qe[0], qe[1], qe[2], qe[3], k[0]);     // columns (0, 2) = lines 0, 2
-            db_filter2(po[0], po[1], po[2], po[3], qo[0], qo[1], qo[2], qo[3], k[1]);     // columns (1, 3) = lines 1, 3
+            db_filter2(pe[0], pe[1], pe[2], pe[3], qe[0], qe[1], qe[2], qe[3], k[0], do3, do4);     // columns (0, 2) = lines 0, 2
+            db_filter2(po[0], po[1], po[2], po[3], qo[0], qo[1], qo[2], qo[3], k[1], do3, do4);     // columns (1, 3) = lines 1, 3
             blk_rowpairs_to_rows(pe, po, rp); blk_rowpairs_to_rows(qe, qo, rq);
             for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) { got[r][c] = (uint8_t)(rp[c] >> (8 * r)); got[r][4 + c] = (uint8_t)(rq[c] >> (8 * r)); }
         }
