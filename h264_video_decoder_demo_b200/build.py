@@ -10,7 +10,7 @@ _ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
 LIB = os.path.join(_PKG, "libh264b2.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "residual.cuh", "residual_kernel.cuh", "inter.cuh", "inter_quad.cuh", "intra.cuh", "deblock.cuh", "deblock_fast.cuh", "deblock_simd.cuh", "simd16.cuh", "wavefront.cuh"]
+HEADERS = ["common.cuh", "residual.cuh", "residual_kernel.cuh", "inter.cuh", "inter_quad.cuh", "inter_tma.cuh", "intra.cuh", "deblock.cuh", "deblock_fast.cuh", "deblock_simd.cuh", "simd16.cuh", "wavefront.cuh"]
 
 
 HOST_LIB = os.path.join(_PKG, "libh264b2_host.so")

@@ -29,7 +29,9 @@ struct alignas(16) PicDev {
     int deblock_enable, deblock_stop;
     int n_weights;
     int generic;                       // 1: MBAFF picture (or wider than 256 MBs): literal per-sample-line paths; 0: progressive fast paths
-    int pad_[3];                       // sizeof(PicDev) is a multiple of 16: the batch prologue copies it as uint4
+    int surf0;                         // index of the stream's surface 0 in the DPB allocation (third coordinate of the TMA tensor maps)
+    int *worklist;                     // [0] = number of entries, [4 ..] = addresses of the inter macroblocks k_inter_tma leaves to k_inter_list
+    int pad_[2];                       // sizeof(PicDev) is a multiple of 16: the batch prologue copies it as uint4
 };
 static_assert(sizeof(PicDev) % 16 == 0, "PicDev must be a multiple of 16 bytes");
 

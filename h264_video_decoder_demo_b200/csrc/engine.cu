@@ -25,6 +25,8 @@
 #include "residual.cuh"
 #include "residual_kernel.cuh"
 #include "inter_quad.cuh"
+#include "inter_tma.cuh"
+#include <cudaTypedefs.h>
 #include "intra.cuh"
 #include "deblock.cuh"
 #include "deblock_simd.cuh"
@@ -212,6 +214,9 @@ struct H264B2Context {
     uint8_t *bgr; size_t bgr_cap;             // BGR24 output staging
     // look-ahead (H264B2_LOOKAHEAD, default on): descriptors, unpacking, k_residual and k_bs of batch i+1 need nothing from batch i,
     // so they run on st_pre while the dependency-bound wavefront kernels of batch i leave issue slots idle; res / bs are double-buffered
+    int *worklist; size_t worklist_stride;    // per stream: entry count + addresses of the macroblocks k_inter_tma leaves to k_inter_list
+    int inter_tma; CUtensorMap map_y, map_c;   // TMA descriptors of the DPB (luma: x, y, surface; chroma: x, y, plane, surface); H264B2_INTER_V1=1 keeps the LDG kernel
+    int debug_launch;                         // H264B2_DEBUG_LAUNCH=1: check for a launch error after every kernel of a batch
     int deblock_v1;                           // H264B2_DEBLOCK_V1=1: first-generation progressive deblocking kernels (A/B runs)
     int lookahead; unsigned batch_no; cudaStream_t st_pre; cudaEvent_t pre_done[DESC_RING], main_done[2];
     size_t bs_stride;                         // words per stream in bs
@@ -354,6 +359,7 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     // writes the records with 16-byte stores (an odd macroblock count would misalign every second stream otherwise)
     c->bs_stride = ((size_t)c->nmb * 65 + 3) & ~(size_t)3;
     { const char *e = getenv("H264B2_LOOKAHEAD"); c->lookahead = !(e && atoi(e) == 0); }
+    { const char *e = getenv("H264B2_DEBUG_LAUNCH"); c->debug_launch = e && atoi(e) != 0; }
     { const char *e = getenv("H264B2_DEBLOCK_V1"); c->deblock_v1 = e && atoi(e) != 0; }
     CK(cudaMalloc(&c->bs, (size_t)n_streams * c->bs_stride * 4 * 2));
     CK(cudaMalloc(&c->res, (size_t)n_streams * c->nmb * RES_MB_STRIDE * 2 * 2));
@@ -404,6 +410,26 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     CK(cudaEventCreate(&c->t0)); CK(cudaEventCreate(&c->t1));
     c->ev = (cudaEvent_t *)calloc(EV_POOL, sizeof(cudaEvent_t));
     if (init_tables(c)) return -10;
+    // tensor maps of the decoded picture buffer for k_inter_tma (global strides must be multiples of 16 bytes: chroma rows need an even width in MBs)
+    { const char *e = getenv("H264B2_INTER_V1"); c->inter_tma = !(e && atoi(e) != 0) && (width_mbs % 2 == 0) && width_mbs <= 256; }
+    c->worklist_stride = ((size_t)c->nmb + 4 + 3) & ~(size_t)3;
+    CK(cudaMalloc(&c->worklist, (size_t)n_streams * c->worklist_stride * sizeof(int)));
+    CK(cudaMemset(c->worklist, 0, (size_t)n_streams * c->worklist_stride * sizeof(int)));
+    if (c->inter_tma) {
+        void *fn = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn || qr != cudaDriverEntryPointSuccess) { cudaGetLastError(); c->inter_tma = 0; }
+        else {
+            PFN_cuTensorMapEncodeTiled enc = (PFN_cuTensorMapEncodeTiled)fn;
+            const cuuint64_t W = (cuuint64_t)width_mbs * 16, H = (cuuint64_t)height_mbs * 16, nsurf = (cuuint64_t)n_streams * surfaces_per_stream;
+            const cuuint64_t dy[3] = { W, H, nsurf }, sy[2] = { W, c->frame_bytes };
+            const cuuint32_t by[3] = { IT_LUMA_PITCH, IT_LUMA_ROWS, 1 }, e3[4] = { 1, 1, 1, 1 };
+            const cuuint64_t dc[4] = { W / 2, H / 2, 2, nsurf }, sc[3] = { W / 2, (W / 2) * (H / 2), c->frame_bytes };
+            const cuuint32_t bc[4] = { IT_CHROMA_PITCH, IT_CHROMA_ROWS, 2, 1 };
+            CUresult r1 = enc(&c->map_y, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->surfaces, dy, sy, by, e3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult r2 = enc(&c->map_c, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, c->surfaces + W * H, dc, sc, bc, e3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return fail(-10, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+        }
+    }
     c->trace_path = getenv("H264B2_TRACE");
     c->trace = c->trace_path != nullptr;
     *out = c;
@@ -415,7 +441,7 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->bgr) cudaFree(c->bgr);
-    cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_pull); for (int i = 0; i < NOUT; i++) cudaFreeHost(c->h_snap[i]);
+    cudaFree(c->worklist); cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_pull); for (int i = 0; i < NOUT; i++) cudaFreeHost(c->h_snap[i]);
     for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->h2d_done2[i]); cudaEventDestroy(c->compute_done[i]); }
     for (int i = 0; i < NOUT; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
     for (int i = 0; i < DESC_RING; i++) { cudaEventDestroy(c->desc_ev[i]); cudaEventDestroy(c->pre_done[i]); }
@@ -465,6 +491,7 @@ static int validate(const H264B2Context *c, int n_pics, const int32_t *sids, con
     return 0;
 }
 
+#define LCHK(name) do { if (c->debug_launch) { cudaError_t e_ = cudaPeekAtLastError(); if (e_ != cudaSuccess) return fail(-10, "launch of %s failed: %s (ng=%d np=%d nq=%d)", name, cudaGetErrorString(e_), ng, np, nq); } } while (0)
 // enqueue the kernels of one batch; every array pointer in pics[] is a device pointer
 static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264B2PicParams *pics, const uint32_t *const *packed = nullptr, const uint32_t *const *packed_motion = nullptr,
                         cudaEvent_t in0 = nullptr, cudaEvent_t in1 = nullptr) {
@@ -493,7 +520,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.bs = c->bs + ((size_t)par * c->n_streams + sids[i]) * c->bs_stride;
         d.res = c->res + ((size_t)par * c->n_streams + sids[i]) * c->nmb * RES_MB_STRIDE;
         d.progress = c->progress + (size_t)sids[i] * 2 * c->hmb;
-        d.frame_bytes = c->frame_bytes;
+        d.frame_bytes = c->frame_bytes; d.surf0 = sids[i] * c->spp; d.worklist = c->worklist + (size_t)sids[i] * c->worklist_stride;
         d.wmb = c->wmb; d.hmb = c->hmb; d.mbaff = p.mbaff_frame_flag; d.cqp0 = p.chroma_qp_offset[0]; d.cqp1 = p.chroma_qp_offset[1];
         d.deblock_enable = p.deblock_enable; d.deblock_stop = p.deblock_stop_mb < c->nmb ? p.deblock_stop_mb : c->nmb;
         d.n_weights = p.n_weights;
@@ -553,7 +580,17 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         }
         if (g_inter) {
             class_begin(c, 1, sg);
-            k_inter<<<dim3((c->wmb + 3) / 4, c->hmb, ng), 128, 0, sg>>>(dg);
+            // progressive pictures (first np descriptors): macroblocks with one vector per list and windows inside the picture go through
+            // the TMA-staged kernel, k_inter does the rest (and everything of MBAFF pictures); the two write disjoint macroblocks
+            if (c->inter_tma && np > 0) {
+                k_zero_worklists<<<1, 256, 0, sg>>>(c->worklist, c->n_streams, c->worklist_stride);
+                k_inter_tma<<<dim3((c->wmb + 4 * IT_MBS - 1) / (4 * IT_MBS), c->hmb, np), 128, 0, sg>>>(dg, c->map_y, c->map_c);
+                LCHK("k_inter_tma");
+                k_inter_list<<<dim3(IT_LIST_CTAS, np), 128, 0, sg>>>(dg);
+                LCHK("k_inter_list");
+                if (nq) k_inter<<<dim3((c->wmb + 3) / 4, c->hmb, nq), 128, 0, sg>>>(dg + np, 0);
+            } else k_inter<<<dim3((c->wmb + 3) / 4, c->hmb, ng), 128, 0, sg>>>(dg, 0);
+            LCHK("k_inter");
             class_end(c, 1, sg);
         }
         // boundary strengths need only side info, not samples: compute them before the wavefronts so that the
@@ -573,6 +610,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         if (np) {
             class_begin(c, 2, sg);
             k_intra<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g);
+            LCHK("k_intra<false>");
             class_end(c, 2, sg);
             if (g_deblock) {
                 class_begin(c, 4, sg);
@@ -584,10 +622,12 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         if (nq) {
             class_begin(c, 2, sq);
             k_intra<true><<<nq * bands, WF_THREADS, 0, sq>>>(dg + np, nq, bands, tickets + 4 * g + 1);
+            LCHK("k_intra<true>");
             class_end(c, 2, sq);
             if (g_deblock) {
                 class_begin(c, 4, sq);
                 k_deblock<true><<<nq * bands, WF_THREADS, 0, sq>>>(dg + np, nq, bands, tickets + 4 * g + 3);
+                LCHK("k_deblock<true>");
                 class_end(c, 4, sq);
             }
             if (sq != sg) { CK(cudaEventRecord(c->side_join[g], sq)); CK(cudaStreamWaitEvent(sg, c->side_join[g], 0)); }

@@ -3,6 +3,7 @@
 #pragma once
 #include "h264_front_internal.h"
 #include <string>
+#include <mutex>
 
 namespace h264b2 {
 
@@ -96,6 +97,7 @@ struct Front {
     // event queue
     std::vector<H264B2FrontEvent> events; size_t ev_pos = 0;
     std::vector<Block> free_blocks, live_blocks;
+    std::mutex block_mu;         // h264b2_front_release() may run on another thread than h264b2_front_next() (decoder facade, multi-stream pipeline)
     uint8_t *get_block(size_t bytes, size_t *cap);
     void release_block(void *p);
     ~Front();

@@ -11,10 +11,12 @@
 namespace h264b2 {
 
 Front::~Front() {
+    std::lock_guard<std::mutex> lk(block_mu);
     for (auto &b : free_blocks) { if (free_fn) free_fn(alloc_user, b.p); else free(b.p); }
     for (auto &b : live_blocks) { if (free_fn) free_fn(alloc_user, b.p); else free(b.p); }
 }
 uint8_t *Front::get_block(size_t bytes, size_t *cap) {
+    std::lock_guard<std::mutex> lk(block_mu);
     for (size_t i = 0; i < free_blocks.size(); i++)
         if (free_blocks[i].cap >= bytes) { Block b = free_blocks[i]; free_blocks.erase(free_blocks.begin() + i); live_blocks.push_back(b); *cap = b.cap; return b.p; }
     const size_t want = (bytes + (1u << 20)) & ~(size_t)((1u << 16) - 1);     // headroom: coefficient volume varies per picture
@@ -24,6 +26,7 @@ uint8_t *Front::get_block(size_t bytes, size_t *cap) {
     return p;
 }
 void Front::release_block(void *p) {
+    std::lock_guard<std::mutex> lk(block_mu);
     for (size_t i = 0; i < live_blocks.size(); i++) if (live_blocks[i].p == p) { free_blocks.push_back(live_blocks[i]); live_blocks.erase(live_blocks.begin() + i); return; }
 }
 

@@ -36,45 +36,13 @@ __device__ __forceinline__ uint32_t pack4_clip(int a, int b, int c, int d, int r
     return pack4(clip255((a + rnd) >> sh), clip255((b + rnd) >> sh), clip255((c + rnd) >> sh), clip255((d + rnd) >> sh));
 }
 
-// Predicted luma row r (8 samples, two packed words) of one quadrant for one list.  (xI, yI): integer position of the
-// quadrant's top-left sample in the reference view.  Called by the 8 lanes of a quadrant together (gmask).
-__device__ __forceinline__ void luma_quad_pred(const uint8_t *base, int stride, int wclamp, int hclamp, int wfast,
-                                               int xI, int yI, int xF, int yF, int r, unsigned gmask,
-                                               uint32_t (*raw)[4], int (*hs)[8], uint32_t out[2]) {
-    const bool fast = xI >= 2 && xI + 14 <= wfast && yI >= 2 && yI + 10 < hclamp;
+// Output row r of a quadrant from its staged window rows (raw) and their unclipped horizontal sums (hs): the half-sample
+// intermediates b/s, h/m, j and the quarter-sample averages of IP:2415-2477.
+__device__ __forceinline__ void luma_quad_combine(const uint32_t (*raw)[4], const int (*hs)[8], int xF, int yF, int r, uint32_t out[2]) {
     const bool needJ = (xF == 2 && yF != 0) || (yF == 2 && xF != 0);
     const bool needH = xF != 0 && yF != 2;
     const bool needV = yF != 0 && xF != 2;
     const int ry = 2 + (yF == 3);
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        const int w = r + 8 * t;
-        if (w < 13 && (yF != 0 || (w >= 2 && w < 10))) {
-            uint32_t A0, A1, A2, A3;
-            if (fast) {
-                const uint8_t *p = base + (size_t)(yI - 2 + w) * stride + (xI - 2);
-                const int o = (int)((uintptr_t)p & 3);
-                const uint32_t *pw = (const uint32_t *)(p - o);
-                const int sh = o * 8;
-                const uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1), w2 = __ldg(pw + 2), w3 = __ldg(pw + 3);
-                A0 = __funnelshift_r(w0, w1, sh); A1 = __funnelshift_r(w1, w2, sh); A2 = __funnelshift_r(w2, w3, sh); A3 = w3 >> sh;
-            } else {
-                const uint8_t *row = base + (size_t)clip3i(0, hclamp - 1, yI - 2 + w) * stride;
-                uint32_t b[13];
-#pragma unroll
-                for (int i = 0; i < 13; i++) b[i] = __ldg(row + clip3i(0, wclamp - 1, xI - 2 + i));
-                A0 = pack4(b[0], b[1], b[2], b[3]); A1 = pack4(b[4], b[5], b[6], b[7]); A2 = pack4(b[8], b[9], b[10], b[11]); A3 = b[12];
-            }
-            *(uint4 *)raw[w] = make_uint4(A0, A1, A2, A3);
-            if (xF != 0 && (needJ || (w >= ry && w < ry + 8))) {
-                int4 ha, hb;
-                tap6x4(A0, A1, A2, ha.x, ha.y, ha.z, ha.w);
-                tap6x4(A1, A2, A3, hb.x, hb.y, hb.z, hb.w);
-                *(int4 *)&hs[w][0] = ha; *(int4 *)&hs[w][4] = hb;
-            }
-        }
-    }
-    __syncwarp(gmask);
     uint32_t G[2] = {0, 0}, Hh[2] = {0, 0}, Vh[2] = {0, 0}, J[2] = {0, 0};
     if (xF == 0 || yF == 0) {                               // full-sample row next to the fractional position
         const uint4 A = *(const uint4 *)raw[r + 2 + (xF == 0 && yF == 3)];
@@ -130,6 +98,48 @@ __device__ __forceinline__ void luma_quad_pred(const uint8_t *base, int stride, 
         else o = avg4(Hh[i], Vh[i]);                                          // e, g, p, r
         out[i] = o;
     }
+}
+
+// Predicted luma row r (8 samples, two packed words) of one quadrant for one list.  (xI, yI): integer position of the
+// quadrant's top-left sample in the reference view.  Called by the 8 lanes of a quadrant together (gmask).
+__device__ __forceinline__ void luma_quad_pred(const uint8_t *base, int stride, int wclamp, int hclamp, int wfast,
+                                               int xI, int yI, int xF, int yF, int r, unsigned gmask,
+                                               uint32_t (*raw)[4], int (*hs)[8], uint32_t out[2]) {
+    const bool fast = xI >= 2 && xI + 14 <= wfast && yI >= 2 && yI + 10 < hclamp;
+    const bool needJ = (xF == 2 && yF != 0) || (yF == 2 && xF != 0);
+    const bool needH = xF != 0 && yF != 2;
+    const bool needV = yF != 0 && xF != 2;
+    const int ry = 2 + (yF == 3);
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int w = r + 8 * t;
+        if (w < 13 && (yF != 0 || (w >= 2 && w < 10))) {
+            uint32_t A0, A1, A2, A3;
+            if (fast) {
+                const uint8_t *p = base + (size_t)(yI - 2 + w) * stride + (xI - 2);
+                const int o = (int)((uintptr_t)p & 3);
+                const uint32_t *pw = (const uint32_t *)(p - o);
+                const int sh = o * 8;
+                const uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1), w2 = __ldg(pw + 2), w3 = __ldg(pw + 3);
+                A0 = __funnelshift_r(w0, w1, sh); A1 = __funnelshift_r(w1, w2, sh); A2 = __funnelshift_r(w2, w3, sh); A3 = w3 >> sh;
+            } else {
+                const uint8_t *row = base + (size_t)clip3i(0, hclamp - 1, yI - 2 + w) * stride;
+                uint32_t b[13];
+#pragma unroll
+                for (int i = 0; i < 13; i++) b[i] = __ldg(row + clip3i(0, wclamp - 1, xI - 2 + i));
+                A0 = pack4(b[0], b[1], b[2], b[3]); A1 = pack4(b[4], b[5], b[6], b[7]); A2 = pack4(b[8], b[9], b[10], b[11]); A3 = b[12];
+            }
+            *(uint4 *)raw[w] = make_uint4(A0, A1, A2, A3);
+            if (xF != 0 && (needJ || (w >= ry && w < ry + 8))) {
+                int4 ha, hb;
+                tap6x4(A0, A1, A2, ha.x, ha.y, ha.z, ha.w);
+                tap6x4(A1, A2, A3, hb.x, hb.y, hb.z, hb.w);
+                *(int4 *)&hs[w][0] = ha; *(int4 *)&hs[w][4] = hb;
+            }
+        }
+    }
+    __syncwarp(gmask);
+    luma_quad_combine(raw, hs, xF, yF, r, out);
     __syncwarp(gmask);                                       // the tile is reused by the next list
 }
 
@@ -165,74 +175,15 @@ __device__ __forceinline__ void chroma_quad_pred(const uint8_t *base, int stride
     p[3] = dp4a_uu(__byte_perm(h0, h1, 0x5410), cf, 32) >> 6;
 }
 
-// grid: (ceil(wmb / 4), hmb, n_pics); block: 128 threads = 4 warps = 4 horizontally consecutive macroblocks (no division
-// to find the macroblock: under MBAFF row 2k / 2k+1 are the top / bottom macroblocks of pair row k).
-#ifndef INTER_MIN_BLOCKS
-#define INTER_MIN_BLOCKS 8
-#endif
-__global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *pics) {
-    __shared__ InterWarpSmem sm[4];
-    const PicDev &P = pics[blockIdx.z];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int mbx = blockIdx.x * 4 + warp, mby = blockIdx.y;
-    if (!P.motion || mbx >= P.wmb) return;
-    const int a = P.mbaff ? 2 * ((mby >> 1) * P.wmb + mbx) + (mby & 1) : mby * P.wmb + mbx;
-    const H264B2MbInfo I = P.info[a];
-    if (I.mb_class != H264B2_MB_INTER) return;
-    const H264B2MbMotion &M = P.motion[a];
-    const int q = lane >> 3, r = lane & 7, qx = (q & 1) * 8, qy = (q >> 1) * 8;
-    const int b0 = (q >> 1) * 8 + (q & 1) * 2;              // raster slot of the quadrant's first 4x4 block
-    const int code0 = M.ref_surf[0][q], code1 = M.ref_surf[1][q];
-    // one vector per list in this quadrant?  (mv[l][slot] = two int16 = one 32-bit word; slots b0, b0+1, b0+4, b0+5)
-    const uint32_t *mvw = (const uint32_t *)&M.mv[0][0][0];
-    uint32_t mv01[2];
-    bool uni = true;
-#pragma unroll
-    for (int l = 0; l < 2; l++) {
-        const uint2 t0 = *(const uint2 *)(mvw + l * 16 + b0), t1 = *(const uint2 *)(mvw + l * 16 + b0 + 4);
-        mv01[l] = t0.x;
-        if ((l ? code1 : code0) >= 0) uni = uni && t0.y == t0.x && t1.x == t0.x && t1.y == t0.x;
-    }
-    if (!__all_sync(0xffffffffu, uni)) {
-        if (lane < 16) inter_block_generic(P, a, P.info[a], lane);
-        return;
-    }
-    const int field = P.mbaff && (I.flags & H264B2_MBF_FIELD);
-    const int ys = field ? 2 : 1;
-    const int x0 = mbx * 16, y0 = !P.mbaff ? mby * 16 : field ? (mby >> 1) * 32 + (mby & 1) : mby * 16;      // mb_origin()
-    const int yA = field ? y0 / 2 : y0;                     // IP:577-580
+// Weighted combination of the lists, residual add and store of this lane's luma row and chroma row (IP:2526-2829, IP:22-407):
+// the tail shared by the clamped routine below and by the TMA-staged kernel (inter_tma.cuh).
+__device__ __forceinline__ void inter_quad_store(const PicDev &P, int a, uint32_t m, int t8, int x0, int y0, int ys, int q, int r,
+                                                 const uint32_t (&pl)[2][2], const int (&pc)[2][4], int have0, int have1, int wt_idx) {
+    const int qx = (q & 1) * 8, qy = (q >> 1) * 8, cpl = r >> 2, cy = r & 3;
     const int W = P.wmb * 16, H = P.hmb * 16, Wc = W >> 1;
-    const unsigned gmask = 0xFFu << (q * 8);
-    const int cpl = r >> 2, cy = r & 3;                     // this lane's chroma plane and chroma row inside the quadrant's block
-
-    uint32_t pl[2][2] = {{0, 0}, {0, 0}};
-    int pc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    const int have0 = code0 >= 0, have1 = code1 >= 0;
-#pragma unroll 1
-    for (int l = 0; l < 2; l++) {
-        const int code = l ? code1 : code0;
-        if (code < 0) continue;
-        RefViewDev rv;
-        ref_view(P, code, rv);
-        const uint32_t mvp = l ? mv01[1] : mv01[0];
-        const int mvx = (int16_t)(mvp & 0xffff), mvy = (int16_t)(mvp >> 16);
-        int mvcy = mvy;
-        if (field) { if (rv.view == 1 && (a & 1)) mvcy += 2; else if (rv.view == 2 && !(a & 1)) mvcy -= 2; }   // IP:2019-2043
-        uint32_t tl[2];
-        int tc[4];
-        luma_quad_pred(rv.base[0], rv.stride[0], rv.wclamp[0], rv.hclamp[0], W, x0 + qx + (mvx >> 2), yA + qy + (mvy >> 2), mvx & 3, mvy & 3,
-                       r, gmask, sm[warp].raw[q], sm[warp].hs[q], tl);
-        const int xC = (x0 + qx) / 2 + (mvx >> 3), yC = (yA + qy) / 2 + (mvcy >> 3) + cy;
-        chroma_quad_pred(cpl ? rv.base[2] : rv.base[1], rv.stride[1], rv.wclamp[1], rv.hclamp[1], Wc, xC, yC, mvx & 7, mvcy & 7, tc);     // Cb and Cr share their geometry
-        if (l == 0) { pl[0][0] = tl[0]; pl[0][1] = tl[1]; pc[0][0] = tc[0]; pc[0][1] = tc[1]; pc[0][2] = tc[2]; pc[0][3] = tc[3]; }
-        else        { pl[1][0] = tl[0]; pl[1][1] = tl[1]; pc[1][0] = tc[0]; pc[1][1] = tc[1]; pc[1][2] = tc[2]; pc[1][3] = tc[3]; }
-    }
     const int none = !have0 && !have1;        // the reference predicts nothing: the residual lands on what the buffer holds
-    const H264B2Weight w = P.weights[M.wt_idx[q]];
-    const uint32_t m = I.coef_mask;
-    const int t8 = (I.flags & H264B2_MBF_T8x8) != 0;
+    const H264B2Weight w = P.weights[wt_idx];
     const int16_t *res = P.res + (size_t)a * RES_MB_STRIDE;
-
     // ---- luma row qy + r, columns qx .. qx+7
     {
         uint8_t *Y = P.dst + (size_t)(y0 + (qy + r) * ys) * W + x0 + qx;
@@ -279,4 +230,105 @@ __global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *p
         }
         *(uint32_t *)C = pack4(v[0], v[1], v[2], v[3]);
     }
+}
+
+// Does a progressive frame macroblock with ONE vector per list (mv0 / mv1, reference codes code0 / code1; -1 = list unused) take the
+// TMA-staged path of inter_tma.cuh?  Frame views only, and every window (21 x 21 luma, 9 x 9 chroma) inside the picture: TMA fills
+// what lies outside with zeros, the reference clamps the coordinates (IP:2363).  Both kernels evaluate this same function.
+__device__ __forceinline__ bool inter_staged_ok(const PicDev &P, int mbx, int mby, int code0, int code1, uint32_t mv0, uint32_t mv1) {
+    if (P.mbaff || P.generic || (code0 < 0 && code1 < 0)) return false;
+    if ((code0 >= 0 && (code0 & 3)) || (code1 >= 0 && (code1 & 3))) return false;
+    const int W = P.wmb * 16, H = P.hmb * 16, x0 = mbx * 16, y0 = mby * 16;
+    bool inside = true;
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+        if ((l ? code1 : code0) < 0) continue;
+        const uint32_t mv = l ? mv1 : mv0;
+        const int mvx = (int16_t)(mv & 0xffffu), mvy = (int16_t)(mv >> 16);
+        const int xI = x0 + (mvx >> 2), yI = y0 + (mvy >> 2), xC = (x0 >> 1) + (mvx >> 3), yC = (y0 >> 1) + (mvy >> 3);
+        inside = inside && xI >= 2 && xI + 18 < W && yI >= 2 && yI + 18 < H && xC >= 0 && xC + 8 < (W >> 1) && yC >= 0 && yC + 8 < (H >> 1);
+    }
+    return inside;
+}
+
+// One inter macroblock by the whole warp with clamped window loads from global memory (any vector, any view, any position).
+__device__ __forceinline__ void inter_mb_ldg(const PicDev &P, int mbx, int mby, int lane, uint32_t (*raw)[13][4], int (*hs)[13][8], int skip_staged) {
+    const int a = P.mbaff ? 2 * ((mby >> 1) * P.wmb + mbx) + (mby & 1) : mby * P.wmb + mbx;
+    const H264B2MbInfo I = P.info[a];
+    if (I.mb_class != H264B2_MB_INTER) return;
+    const H264B2MbMotion &M = P.motion[a];
+    const int q = lane >> 3, r = lane & 7, qx = (q & 1) * 8, qy = (q >> 1) * 8;
+    const int b0 = (q >> 1) * 8 + (q & 1) * 2;              // raster slot of the quadrant's first 4x4 block
+    const int code0 = M.ref_surf[0][q], code1 = M.ref_surf[1][q];
+    // one vector per list in this quadrant?  (mv[l][slot] = two int16 = one 32-bit word; slots b0, b0+1, b0+4, b0+5)
+    const uint32_t *mvw = (const uint32_t *)&M.mv[0][0][0];
+    uint32_t mv01[2];
+    bool uni = true;
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+        const uint2 t0 = *(const uint2 *)(mvw + l * 16 + b0), t1 = *(const uint2 *)(mvw + l * 16 + b0 + 4);
+        mv01[l] = t0.x;
+        if ((l ? code1 : code0) >= 0) uni = uni && t0.y == t0.x && t1.x == t0.x && t1.y == t0.x;
+    }
+    if (!__all_sync(0xffffffffu, uni)) {
+        if (lane < 16) inter_block_generic(P, a, P.info[a], lane);
+        return;
+    }
+    if (skip_staged) {
+        // macroblocks that k_inter_tma reconstructs (one vector, one reference pair, one weight entry for the whole macroblock, windows
+        // inside the picture) are not touched here
+        const uint32_t key0 = code0 >= 0 ? mv01[0] : 0u, key1 = code1 >= 0 ? mv01[1] : 0u, wti = M.wt_idx[q];
+        // every shuffle is executed by all lanes (no short-circuit in front of a warp-collective)
+        const int c0 = __shfl_sync(0xffffffffu, code0, 0), c1 = __shfl_sync(0xffffffffu, code1, 0);
+        const uint32_t k0 = __shfl_sync(0xffffffffu, key0, 0), k1 = __shfl_sync(0xffffffffu, key1, 0), w0 = __shfl_sync(0xffffffffu, wti, 0);
+        const uint32_t m0 = __shfl_sync(0xffffffffu, mv01[0], 0), m1 = __shfl_sync(0xffffffffu, mv01[1], 0);
+        const bool same = (code0 == c0) & (code1 == c1) & (key0 == k0) & (key1 == k1) & (wti == w0);
+        const bool all_same = __all_sync(0xffffffffu, same);
+        if (all_same && inter_staged_ok(P, mbx, mby, c0, c1, m0, m1)) return;
+    }
+    const int field = P.mbaff && (I.flags & H264B2_MBF_FIELD);
+    const int ys = field ? 2 : 1;
+    const int x0 = mbx * 16, y0 = !P.mbaff ? mby * 16 : field ? (mby >> 1) * 32 + (mby & 1) : mby * 16;      // mb_origin()
+    const int yA = field ? y0 / 2 : y0;                     // IP:577-580
+    const int W = P.wmb * 16, Wc = W >> 1;
+    const unsigned gmask = 0xFFu << (q * 8);
+    const int cpl = r >> 2, cy = r & 3;                     // this lane's chroma plane and chroma row inside the quadrant's block
+
+    uint32_t pl[2][2] = {{0, 0}, {0, 0}};
+    int pc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    const int have0 = code0 >= 0, have1 = code1 >= 0;
+#pragma unroll 1
+    for (int l = 0; l < 2; l++) {
+        const int code = l ? code1 : code0;
+        if (code < 0) continue;
+        RefViewDev rv;
+        ref_view(P, code, rv);
+        const uint32_t mvp = l ? mv01[1] : mv01[0];
+        const int mvx = (int16_t)(mvp & 0xffff), mvy = (int16_t)(mvp >> 16);
+        int mvcy = mvy;
+        if (field) { if (rv.view == 1 && (a & 1)) mvcy += 2; else if (rv.view == 2 && !(a & 1)) mvcy -= 2; }   // IP:2019-2043
+        uint32_t tl[2];
+        int tc[4];
+        luma_quad_pred(rv.base[0], rv.stride[0], rv.wclamp[0], rv.hclamp[0], W, x0 + qx + (mvx >> 2), yA + qy + (mvy >> 2), mvx & 3, mvy & 3,
+                       r, gmask, raw[q], hs[q], tl);
+        const int xC = (x0 + qx) / 2 + (mvx >> 3), yC = (yA + qy) / 2 + (mvcy >> 3) + cy;
+        chroma_quad_pred(cpl ? rv.base[2] : rv.base[1], rv.stride[1], rv.wclamp[1], rv.hclamp[1], Wc, xC, yC, mvx & 7, mvcy & 7, tc);     // Cb and Cr share their geometry
+        if (l == 0) { pl[0][0] = tl[0]; pl[0][1] = tl[1]; pc[0][0] = tc[0]; pc[0][1] = tc[1]; pc[0][2] = tc[2]; pc[0][3] = tc[3]; }
+        else        { pl[1][0] = tl[0]; pl[1][1] = tl[1]; pc[1][0] = tc[0]; pc[1][1] = tc[1]; pc[1][2] = tc[2]; pc[1][3] = tc[3]; }
+    }
+    inter_quad_store(P, a, I.coef_mask, (I.flags & H264B2_MBF_T8x8) != 0, x0, y0, ys, q, r, pl, pc, have0, have1, M.wt_idx[q]);
+}
+
+// grid: (ceil(wmb / 4), hmb, n_pics); block: 128 threads = 4 warps = 4 horizontally consecutive macroblocks (no division
+// to find the macroblock: under MBAFF row 2k / 2k+1 are the top / bottom macroblocks of pair row k).
+#ifndef INTER_MIN_BLOCKS
+#define INTER_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, INTER_MIN_BLOCKS) k_inter(const PicDev *pics, int skip_staged) {
+    __shared__ InterWarpSmem sm[4];
+    const PicDev &P = pics[blockIdx.z];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mbx = blockIdx.x * 4 + warp, mby = blockIdx.y;
+    if (!P.motion || mbx >= P.wmb) return;
+    inter_mb_ldg(P, mbx, mby, lane, sm[warp].raw, sm[warp].hs, skip_staged);
 }

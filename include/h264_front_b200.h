@@ -69,6 +69,8 @@ int h264b2_front_open_range(H264B2Front *f, const uint8_t *data, size_t bytes, s
 /* Pull the next event. Returns 0, or <0 on a fatal stream error (message in h264b2_front_last_error). */
 int h264b2_front_next(H264B2Front *f, H264B2FrontEvent *ev);
 /* Give a picture block back for reuse (blocks still out at destroy time are freed there). */
+/* Thread safety: h264b2_front_release() may be called from another thread while h264b2_front_next() runs on the same front end
+ * (the block pool is locked); every other call on one front end must come from one thread at a time. */
 int h264b2_front_release(H264B2Front *f, void *block);
 const char *h264b2_front_last_error(H264B2Front *f);
 /* Convenience for tools/tests: parse a whole stream into a picture container file (same format the reference harness writes). */

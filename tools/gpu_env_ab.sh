@@ -5,5 +5,5 @@ mkdir -p gpurun_out
 i=0
 for v in "$@"; do
   i=$((i+1))
-  env $v timeout 600 python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu --no-bitstream > gpurun_out/env_$TAG.v$i.json 2> gpurun_out/env_$TAG.v$i.err
+  env $v timeout 240 python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu --no-bitstream > gpurun_out/env_$TAG.v$i.json 2> gpurun_out/env_$TAG.v$i.err
 done

@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 for lib in "$@"; do
   n=$(basename $lib .so)
   if [ "$lib" = default ]; then
-    timeout 600 python bench.py --streams $S --steps 1 --warmup 1 --no-e2e --no-cpu --no-bitstream > gpurun_out/lib_$TAG.$n.json 2> gpurun_out/lib_$TAG.$n.err
+    timeout 240 python bench.py --streams $S --steps 1 --warmup 1 --no-e2e --no-cpu --no-bitstream > gpurun_out/lib_$TAG.$n.json 2> gpurun_out/lib_$TAG.$n.err
   else
-    H264B2_LIB=$PWD/$lib timeout 600 python bench.py --streams $S --steps 1 --warmup 1 --no-e2e --no-cpu --no-bitstream > gpurun_out/lib_$TAG.$n.json 2> gpurun_out/lib_$TAG.$n.err
+    H264B2_LIB=$PWD/$lib timeout 240 python bench.py --streams $S --steps 1 --warmup 1 --no-e2e --no-cpu --no-bitstream > gpurun_out/lib_$TAG.$n.json 2> gpurun_out/lib_$TAG.$n.err
   fi
 done
