@@ -31,7 +31,8 @@ struct alignas(16) PicDev {
     int generic;                       // 1: MBAFF picture (or wider than 256 MBs): literal per-sample-line paths; 0: progressive fast paths
     int surf0;                         // index of the stream's surface 0 in the DPB allocation (third coordinate of the TMA tensor maps)
     int *worklist;                     // [0] = number of entries, [4 ..] = addresses of the inter macroblocks k_inter_tma leaves to k_inter_list
-    int pad_[2];                       // sizeof(PicDev) is a multiple of 16: the batch prologue copies it as uint4
+    int spp;                           // DPB surfaces per stream: reference codes are clamped to it (a corrupt SoA must not reach another stream's DPB)
+    uint32_t n_coefs;                  // int16 elements behind coefs: macroblocks whose blocks would lie beyond it are treated as uncoded
 };
 static_assert(sizeof(PicDev) % 16 == 0, "PicDev must be a multiple of 16 bytes");
 
@@ -131,6 +132,18 @@ __device__ inline int nbr_sample(const PicDev &P, int cur, int xN, int yN, int c
     if (comp == 0) return __ldcg(P.dst + (size_t)(y0 + (f ? 2 * yW : yW)) * W + x0 + xW);
     const uint8_t *pl = P.dst + (size_t)W * H + (comp == 2 ? (size_t)(W / 2) * (H / 2) : 0);
     return __ldcg(pl + (size_t)(chroma_y0(y0) + (f ? 2 * yW : yW)) * (W / 2) + (x0 >> 1) + xW);
+}
+
+// ---- bounds of host-supplied indices (the pre-parsed container path reads them straight from a file) ----
+// int16 elements the coefficient blocks of a macroblock occupy (include/h264_recon_b200.h: coef_mask)
+__device__ __forceinline__ uint32_t mb_coef_count(uint32_t m, int cls, int t8flag) {
+    if (m & H264B2_CM_PCM) return 384u;
+    const int t8 = t8flag && cls != H264B2_MB_I16x16;
+    return (uint32_t)(__popc(m & 0xFFFFu) * (t8 ? 64 : 16) + ((m >> 16) & 1u) * 16 + ((m >> 17) & 1u) * 8 + __popc((m >> 18) & 0xFFu) * 16);
+}
+__device__ __forceinline__ bool mb_coefs_in_bounds(const PicDev &P, int a, uint32_t m, int cls, int t8flag) {
+    const unsigned long long end = (unsigned long long)P.coef_off[a] + mb_coef_count(m, cls, t8flag);
+    return end <= (unsigned long long)P.n_coefs;
 }
 
 // ---- chroma QP (PB:4748; table PB:4773) ----

@@ -339,6 +339,7 @@ extern "C" uint64_t h264b2_checksum_host(const uint8_t *data, size_t bytes) {
     return acc;
 }
 
+static int create_impl(H264B2Context *c, int device, int n_streams, int surfaces_per_stream, int width_mbs, int height_mbs);
 extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int surfaces_per_stream, int width_mbs, int height_mbs) {
     if (!out || n_streams < 1 || surfaces_per_stream < 1 || surfaces_per_stream > 32 || width_mbs < 1 || height_mbs < 1)
         return fail(-1, "h264b2_create: bad argument");
@@ -349,6 +350,18 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     H264B2Context *c = new (std::nothrow) H264B2Context();
     if (!c) return fail(-12, "out of memory");
     memset(c, 0, sizeof *c);
+    const int rc = create_impl(c, device, n_streams, surfaces_per_stream, width_mbs, height_mbs);
+    if (rc) {                                   // release whatever was created before the failing call (the error text stays)
+        char keep[sizeof g_err]; memcpy(keep, g_err, sizeof keep);
+        h264b2_destroy(c);
+        cudaGetLastError();
+        memcpy(g_err, keep, sizeof keep);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+static int create_impl(H264B2Context *c, int device, int n_streams, int surfaces_per_stream, int width_mbs, int height_mbs) {
     c->device = device; c->n_streams = n_streams; c->spp = surfaces_per_stream; c->wmb = width_mbs; c->hmb = height_mbs;
     c->nmb = width_mbs * height_mbs; c->frame_bytes = (size_t)c->nmb * 384;
     const size_t total = (size_t)n_streams * surfaces_per_stream * c->frame_bytes;
@@ -432,27 +445,28 @@ extern "C" int h264b2_create(H264B2Context **out, int device, int n_streams, int
     }
     c->trace_path = getenv("H264B2_TRACE");
     c->trace = c->trace_path != nullptr;
-    *out = c;
     return 0;
 }
 
+static void ev_destroy(cudaEvent_t e) { if (e) cudaEventDestroy(e); }
+static void st_destroy(cudaStream_t st) { if (st) cudaStreamDestroy(st); }
 extern "C" int h264b2_destroy(H264B2Context *c) {
     if (!c) return fail(-1, "null context");
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->bgr) cudaFree(c->bgr);
     cudaFree(c->worklist); cudaFree(c->surfaces); cudaFree(c->bs); cudaFree(c->res); cudaFree(c->progress); cudaFree(c->ls_flat); cudaFree(c->d_desc); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_pull); for (int i = 0; i < NOUT; i++) cudaFreeHost(c->h_snap[i]);
-    for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); cudaEventDestroy(c->h2d_done[i]); cudaEventDestroy(c->h2d_done2[i]); cudaEventDestroy(c->compute_done[i]); }
-    for (int i = 0; i < NOUT; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); cudaEventDestroy(c->out_ready[i]); cudaEventDestroy(c->out_done[i]); }
-    for (int i = 0; i < DESC_RING; i++) { cudaEventDestroy(c->desc_ev[i]); cudaEventDestroy(c->pre_done[i]); }
-    cudaEventDestroy(c->main_done[0]); cudaEventDestroy(c->main_done[1]); cudaStreamDestroy(c->st_pre);
+    for (int i = 0; i < NSLOT; i++) { if (c->arena[i]) cudaFree(c->arena[i]); ev_destroy(c->h2d_done[i]); ev_destroy(c->h2d_done2[i]); ev_destroy(c->compute_done[i]); }
+    for (int i = 0; i < NOUT; i++) { if (c->out_stage[i]) cudaFree(c->out_stage[i]); ev_destroy(c->out_ready[i]); ev_destroy(c->out_done[i]); }
+    for (int i = 0; i < DESC_RING; i++) { ev_destroy(c->desc_ev[i]); ev_destroy(c->pre_done[i]); }
+    ev_destroy(c->main_done[0]); ev_destroy(c->main_done[1]); st_destroy(c->st_pre);
     cudaFree(c->d_ptrs); cudaFree(c->d_sums); cudaFreeHost(c->h_sums); cudaFreeHost(c->h_ptrs);
-    for (int i = 0; i < EV_POOL; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->ev) { for (int i = 0; i < EV_POOL; i++) if (c->ev[i]) ev_destroy(c->ev[i]); }
     free(c->ev);
-    cudaEventDestroy(c->t0); cudaEventDestroy(c->t1);
-    cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_h2d2); cudaStreamDestroy(c->st_d2h);
-    for (int i = 0; i < MAX_GROUPS; i++) { cudaStreamDestroy(c->st_g[i]); cudaStreamDestroy(c->st_side[i]); cudaEventDestroy(c->join_ev[i]); cudaEventDestroy(c->side_fork[i]); cudaEventDestroy(c->side_join[i]); }
-    cudaEventDestroy(c->fork_ev);
+    ev_destroy(c->t0); ev_destroy(c->t1);
+    st_destroy(c->st); st_destroy(c->st_h2d); st_destroy(c->st_h2d2); st_destroy(c->st_d2h);
+    for (int i = 0; i < MAX_GROUPS; i++) { st_destroy(c->st_g[i]); st_destroy(c->st_side[i]); ev_destroy(c->join_ev[i]); ev_destroy(c->side_fork[i]); ev_destroy(c->side_join[i]); }
+    ev_destroy(c->fork_ev);
     delete c;
     return 0;
 }
@@ -523,7 +537,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.frame_bytes = c->frame_bytes; d.surf0 = sids[i] * c->spp; d.worklist = c->worklist + (size_t)sids[i] * c->worklist_stride;
         d.wmb = c->wmb; d.hmb = c->hmb; d.mbaff = p.mbaff_frame_flag; d.cqp0 = p.chroma_qp_offset[0]; d.cqp1 = p.chroma_qp_offset[1];
         d.deblock_enable = p.deblock_enable; d.deblock_stop = p.deblock_stop_mb < c->nmb ? p.deblock_stop_mb : c->nmb;
-        d.n_weights = p.n_weights;
+        d.n_weights = p.n_weights; d.spp = c->spp; d.n_coefs = p.n_coefs;
         d.generic = p.mbaff_frame_flag || c->wmb > 256;
         n_prog += !d.generic;
         any_inter |= p.has_inter; any_deblock |= p.deblock_enable;
@@ -748,6 +762,15 @@ extern "C" int h264b2_submit(H264B2Context *c, int n_pics, const int32_t *sids, 
     int r = validate(c, n_pics, sids, pics);
     if (r) return r;
     CK(cudaSetDevice(c->device));
+    // every check that can fail comes BEFORE an arena slot is taken: a rejected submit must not shift the H264B2_SUBMIT_DEPTH contract
+    for (int i = 0; i < n_pics; i++) {
+        const H264B2PicParams &p = pics[i];
+        const size_t nmb = (size_t)c->nmb;
+        if ((p.packed & H264B2_PACKED_MOTION) && p.has_inter && !blob_header_ok((const uint32_t *)p.motion, (uint32_t)((nmb * (sizeof(H264B2MbMotion) / 2) + 15) / 16)))
+            return fail(-3, "submit: malformed packed motion blob (picture %d)", i);
+        if ((p.packed & H264B2_PACKED_COEFS) && p.n_coefs && !blob_header_ok((const uint32_t *)p.coefs, (p.n_coefs + 15) / 16))
+            return fail(-3, "submit: malformed packed coefficient blob (picture %d)", i);
+    }
     const int slot = c->slot_next; c->slot_next = (c->slot_next + 1) % NSLOT;
     CK(cudaEventSynchronize(c->h2d_done[slot]));      // the host arrays of the submit NSLOT calls ago have left (API contract)
     if (c->h2d_streams > 1) CK(cudaEventSynchronize(c->h2d_done2[slot]));

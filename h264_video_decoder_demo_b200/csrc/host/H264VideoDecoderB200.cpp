@@ -69,6 +69,7 @@ int CH264VideoDecoderB200::open(const char *url) {
             Pic pc; memset(&pc, 0, sizeof pc);
             if (off + sizeof(PicHdr) > (size_t)total) FAIL(-1, "open: truncated container");
             memcpy(&pc.h, blob + off, sizeof(PicHdr)); off += sizeof(PicHdr);
+            if (pc.h.n_weights < 1 || pc.h.n_weights > 65536 || (size_t)pc.h.n_coefs > (size_t)total / 2) FAIL(-1, "open: corrupt picture header %u", i);
             H264B2PicParams &p = pc.p;
             p.width_mbs = (int)fh.width_mbs; p.height_mbs = (int)fh.height_mbs; p.mbaff_frame_flag = pc.h.mbaff;
             p.chroma_qp_offset[0] = pc.h.cqp0; p.chroma_qp_offset[1] = pc.h.cqp1;

@@ -58,7 +58,7 @@ int Front::pump() {
             }
             if (!rbsp.empty()) rbsp.back() &= 0xFE;
             const size_t nbytes = rbsp.size(); rbsp.resize(nbytes + 16, 0); br.init(rbsp.data(), nbytes);
-            if (t == 7) { SPS sp; parse_sps(br, sp); if (sp.sps_id >= 0 && sp.sps_id < 32) { spss[sp.sps_id] = sp; max_num_reorder_frames = sp.max_num_reorder_frames; sps_seen = 1; } }
+            if (t == 7) { SPS sp; parse_sps(br, sp); if (sp.valid && sp.sps_id >= 0 && sp.sps_id < 32) { spss[sp.sps_id] = sp; max_num_reorder_frames = sp.max_num_reorder_frames; sps_seen = 1; } }
             else { PPS pp; if (parse_pps(br, pp, spss) != -2 && pp.pps_id >= 0 && pp.pps_id < 256) { ppss[pp.pps_id] = pp; pps_seen = 1; } }
         }
         nal_pos = range_begin;
@@ -103,7 +103,7 @@ int Front::pump() {
             int r = handle_slice_nal(nal_ref_idc, nal_unit_type);
             if (r < 0) return r;
             break; }
-        case 7: { SPS s; parse_sps(br, s); if (s.sps_id >= 0 && s.sps_id < 32) { spss[s.sps_id] = s; max_num_reorder_frames = s.max_num_reorder_frames; sps_seen = 1; } break; }
+        case 7: { SPS s; parse_sps(br, s); if (s.valid && s.sps_id >= 0 && s.sps_id < 32) { spss[s.sps_id] = s; max_num_reorder_frames = s.max_num_reorder_frames; sps_seen = 1; } break; }
         case 8: { PPS p; int r = parse_pps(br, p, spss); if (r == -2) { error = "slice groups (FMO) are not supported"; return -1; } if (p.pps_id >= 0 && p.pps_id < 256) { ppss[p.pps_id] = p; pps_seen = 1; } break; }
         case 2: case 3: case 4: error = "data partitioning NAL units are not supported"; return -1;
         default: break;

@@ -72,6 +72,10 @@ int parse_sps(BitReader &br, SPS &s) {
         br.u1();
         if (br.u1()) { br.u1(); br.ue(); br.ue(); br.ue(); br.ue(); s.max_num_reorder_frames = (int)br.ue(); br.ue(); }
     }
+    // untrusted fields: ue() returns 0xFFFFFFFF for an invalid code, which would make the sizes below 0 (division by zero in the level
+    // table look-up) or overflow the macroblock count; the log2 fields are shift counts (7.4.2.1.1: 0..12)
+    if ((uint32_t)s.pic_width_in_mbs_minus1 >= 1024u || (uint32_t)s.pic_height_in_map_units_minus1 >= 1024u) return -1;
+    if ((uint32_t)s.log2_max_frame_num_minus4 > 12u || (uint32_t)s.log2_max_pic_order_cnt_lsb_minus4 > 12u) return -1;
     s.PicWidthInMbs = s.pic_width_in_mbs_minus1 + 1; s.PicHeightInMapUnits = s.pic_height_in_map_units_minus1 + 1;
     s.FrameHeightInMbs = (2 - s.frame_mbs_only_flag) * s.PicHeightInMapUnits;
     if (s.max_num_reorder_frames == -1) {      // H264SPS.cpp:371-397: derive from the level's MaxDpbMbs

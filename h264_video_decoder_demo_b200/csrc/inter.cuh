@@ -26,7 +26,7 @@ struct RefViewDev {
 // IP:2117 result code -> addressing (field views: PB:183-230; clamps IP:2351-2363, 2492-2512; Q4: a field
 // view keeps the doubled stride as its width)
 __device__ __forceinline__ void ref_view(const PicDev &P, int code, RefViewDev &rv) {
-    const int slot = code >> 2, view = code & 3;
+    const int slot = min(code >> 2, P.spp - 1), view = code & 3;
     const int W = P.wmb * 16, H = P.hmb * 16, Wc = W >> 1, Hc = H >> 1;
     const uint8_t *s = P.stream_base + (size_t)slot * P.frame_bytes;
     const uint8_t *pl[3] = { s, s + (size_t)W * H, s + (size_t)W * H + (size_t)Wc * Hc };
@@ -255,7 +255,7 @@ __device__ __noinline__ void inter_block_generic(const PicDev &P, int a, const H
     uint8_t *C0 = P.dst + (size_t)W * H + (size_t)(chroma_y0(y0) + (by / 2) * ys) * Wc + (x0 >> 1) + bx / 2;
     uint8_t *C1 = C0 + (size_t)Wc * (H >> 1);
     const int none = !have[0] && !have[1];     // the reference predicts nothing: the residual lands on what the buffer holds
-    const H264B2Weight w = P.weights[M.wt_idx[q]];
+    const H264B2Weight w = P.weights[min((int)M.wt_idx[q], P.n_weights - 1)];
     const uint32_t m = I.coef_mask;
     const int t8 = (I.flags & H264B2_MBF_T8x8) != 0;
     const int16_t *res = P.res + (size_t)a * RES_MB_STRIDE;

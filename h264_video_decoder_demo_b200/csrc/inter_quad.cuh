@@ -182,7 +182,7 @@ __device__ __forceinline__ void inter_quad_store(const PicDev &P, int a, uint32_
     const int qx = (q & 1) * 8, qy = (q >> 1) * 8, cpl = r >> 2, cy = r & 3;
     const int W = P.wmb * 16, H = P.hmb * 16, Wc = W >> 1;
     const int none = !have0 && !have1;        // the reference predicts nothing: the residual lands on what the buffer holds
-    const H264B2Weight w = P.weights[wt_idx];
+    const H264B2Weight w = P.weights[min(wt_idx, P.n_weights - 1)];
     const int16_t *res = P.res + (size_t)a * RES_MB_STRIDE;
     // ---- luma row qy + r, columns qx .. qx+7
     {

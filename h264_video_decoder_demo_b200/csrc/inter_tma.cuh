@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128, IT_MIN_BLOCKS) k_inter_tma(const PicDev *
             const uint32_t mv = l ? m.mv1 : m.mv0;
             const int mvx = (int16_t)(mv & 0xffffu), mvy = (int16_t)(mv >> 16);
             const uint32_t dst = smem_addr(&S.tile[st][l][0]);
-            const int surf = P.surf0 + (code >> 2);
+            const int surf = P.surf0 + min(code >> 2, P.spp - 1);
             tma_load_3d(dst, map_y, (x0 + (mvx >> 2) - 2) & ~15, y0 + (mvy >> 2) - 2, surf, bar);
             tma_load_4d(dst + IT_LUMA_BYTES, map_c, ((x0 >> 1) + (mvx >> 3)) & ~15, (y0 >> 1) + (mvy >> 3), 0, surf, bar);
         }

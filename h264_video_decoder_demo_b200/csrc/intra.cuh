@@ -174,6 +174,7 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     uint8_t *Y = P.dst, *Cb = P.dst + (size_t)W * H, *Cr = Cb + (size_t)Wc * (H >> 1);
     const int cls = I.mb_class;
     if (cls == H264B2_MB_IPCM) {                                       // PB:2449
+        if (!mb_coefs_in_bounds(P, a, H264B2_CM_PCM, cls, 0)) return;      // samples beyond the coefficient array: leave the buffer as it is
         const int16_t *pcm = P.coefs + P.coef_off[a];
         for (int i = lane; i < 256; i += 32) Y[(size_t)(y0 + ys * (i >> 4)) * W + x0 + (i & 15)] = (uint8_t)pcm[i];
         for (int i = lane; i < 64; i += 32) {

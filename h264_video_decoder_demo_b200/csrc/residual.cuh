@@ -111,8 +111,8 @@ struct SyncCta  { __device__ __forceinline__ void operator()() const { __syncthr
 // tid/nthreads: the cooperating group; sync() must be a barrier for exactly that group.
 template <class Sync>
 __device__ inline void mb_residual(const PicDev &P, int a, const H264B2MbInfo &I, int tid, int nthreads, ResidualTile &T, Sync sync) {
-    const uint32_t m = I.coef_mask;
     const int cls = I.mb_class;
+    const uint32_t m = mb_coefs_in_bounds(P, a, I.coef_mask, cls, I.flags & H264B2_MBF_T8x8) ? I.coef_mask : 0u;
     const int inter = cls == H264B2_MB_INTER;
     const int sf = (I.flags & H264B2_MBF_FIELD) ? 1 : 0;     // field_pic_flag | mb_field_decoding_flag (PB:3419)
     const int t8 = (I.flags & H264B2_MBF_T8x8) && cls != H264B2_MB_I16x16;

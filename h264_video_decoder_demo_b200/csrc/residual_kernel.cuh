@@ -45,8 +45,10 @@ __global__ void __launch_bounds__(256) k_residual(const PicDev *pics) {
     if (a >= P.wmb * P.hmb) return;
     const H264B2MbInfo I = P.info[a];
     if (!mb_has_residual(I)) return;
-    const uint32_t m = I.coef_mask;
     const int cls = I.mb_class;
+    // blocks that would lie beyond the coefficient array (corrupt offsets) are treated as uncoded
+    const uint32_t m = mb_coefs_in_bounds(P, a, I.coef_mask, cls, I.flags & H264B2_MBF_T8x8) ? I.coef_mask : 0u;
+    if (m == 0u && cls == H264B2_MB_INTER) return;
     const int inter = cls == H264B2_MB_INTER;
     const int sf = (I.flags & H264B2_MBF_FIELD) ? 1 : 0;     // field_pic_flag | mb_field_decoding_flag (PB:3419)
     const int t8 = (I.flags & H264B2_MBF_T8x8) && cls != H264B2_MB_I16x16;

@@ -69,9 +69,21 @@ def closed_gop_starts(rp) -> List[int]:
     independently of everything before it.  The replay container does not carry nal_unit_type; an IDR is
     recognised as an I picture whose PicOrderCnt is 0 and which no later picture precedes in output order."""
     starts = []
+    # output position of every decode index; a picture that is never output (truncated stream) sorts last
+    pos = {d: k for k, d in enumerate(getattr(rp, "out_order", []) or [])}
+    n = len(rp.pictures)
+    big = len(pos) + n
+    opos = [pos.get(p.decode_idx, big + i) for i, p in enumerate(rp.pictures)]
+    # suffix minimum of the output positions: picture i opens a closed GOP only if everything decoded before it is output before
+    # everything decoded from it on (a non-IDR I picture with POC 0, e.g. after MMCO5, fails this when B pictures straddle it)
+    suf = [big + n] * (n + 1)
+    for i in range(n - 1, -1, -1):
+        suf[i] = min(suf[i + 1], opos[i])
+    pre = -1
     for i, p in enumerate(rp.pictures):
-        if p.slice_type % 5 == 2 and p.poc == 0 and p.has_inter == 0:
+        if p.slice_type % 5 == 2 and p.poc == 0 and p.has_inter == 0 and pre < suf[i]:
             starts.append(i)
+        pre = max(pre, opos[i])
     if not starts or starts[0] != 0:
         starts.insert(0, 0)
     return starts
