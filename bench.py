@@ -172,6 +172,54 @@ def algorithmic_bytes(rp):
     return out
 
 
+def measure_config(name, stems_, S, local_rank, world, max_pictures=None):
+    """Short device-timed measurement of another BASELINE.json configuration (one warm-up pass that is checked against the reference's
+    checksums, one timed pass): value in frames/s over all ranks, and whether parity was checked on full streams."""
+    import numpy as np
+    from h264_video_decoder_demo_b200 import engine, replay, sharding
+    eng, vs, full_all = None, [], True
+    for st in stems_:
+        path, full = find_replay(st)
+        full_all &= full
+        rpv = replay.load_replay(path) if max_pictures is None else replay.parse_replay(replay.read_replay_bytes(path), path, max_pictures)
+        if eng is None:
+            eng = engine.Engine(local_rank, S, rpv.width_mbs, rpv.height_mbs)
+        vs.append({"rp": rpv, "rs": None})
+    sids = list(range(S))
+    var_of = [s % len(vs) for s in sids]
+    rs = []
+    for s in sids:
+        v = vs[var_of[s]]
+        if v["rs"] is None:
+            v["rs"] = engine.ResidentStream(eng, v["rp"]); rs.append(v["rs"])
+        else:
+            rs.append(v["rs"].clone())
+    npic = max(len(v["rp"].pictures) for v in vs)
+    pic_of = lambda s, i: i % len(vs[var_of[s]]["rp"].pictures)
+    batches = [eng.prepare(sids, [rs[s].params[pic_of(s, i)] for s in sids]) for i in range(npic)]
+    dst = [[vs[var_of[s]]["rp"].pictures[pic_of(s, i)].dst_surface for s in sids] for i in range(npic)]
+    want = [[vs[var_of[s]]["rp"].pictures[pic_of(s, i)].sum_post for s in sids] for i in range(npic)]
+    ok = True
+    for i, b in enumerate(batches):                 # warm-up pass, every picture of every stream checked
+        eng.submit_prepared(b)
+        ok &= eng.checksums(sids, dst[i]) == want[i]
+    eng.sync()
+    sharding.barrier()
+    eng.timer_start()
+    for b in batches:
+        eng.submit_prepared(b)
+    ms = sharding.max_over_ranks(eng.timer_stop())
+    kt = eng.kernel_times()
+    for r_ in rs:
+        r_.free()
+    eng.close()
+    if not ok:
+        raise SystemExit(f"PARITY FAILURE in configuration {name}")
+    return {"value": round(S * npic * world / (ms / 1000.0), 1), "unit": UNIT, "streams_per_gpu": S, "pictures_per_pass_per_gpu": S * npic,
+            "ms_per_pass": round(ms, 1), "parity": "every picture of every stream equals the reference's checksum" + ("" if full_all else " (golden prefixes)"),
+            "kernel_ms": {k: round(v["ms"], 1) for k, v in kt.items()}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +235,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--host-layout", default="shared", choices=["batch", "shared"], help="e2e: picture blocks of a submit back to back in pinned memory (one DMA per batch) or one block per distinct picture")
     ap.add_argument("--dense-coefs", action="store_true", help="e2e: send plain arrays (dense int16 levels, full motion records) instead of the packed transport")
+    ap.add_argument("--no-pack-in-e2e", action="store_true", help="e2e: pack levels / motion once before the timed region instead of for every submitted picture inside it")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short measurements of the other BASELINE.json configurations (tff, gop121, mixed)")
     ap.add_argument("--no-bitstream", action="store_true", help="skip the Annex-B-in / frames-out pipeline measurement")
     ap.add_argument("--bitstream-streams", type=int, default=32, help="streams per GPU of the Annex-B pipeline measurement")
     ap.add_argument("--bitstream-threads", type=int, default=0, help="parser threads (0 = usable host cores / ranks)")
@@ -402,15 +452,21 @@ def main():
                       "algorithmic_gb_per_step": round(per_step[k] / 1e9, 4),
                       "achieved_gbs": round(per_step[k] * kt_steps / (t / 1000.0) / 1e9, 1) if t > 0 else None}
     achieved = kernels[dom]["achieved_gbs"]
-    traffic = None
+    # DRAM traffic of the dominant kernel from the ncu --set full capture of THIS build (tools/gpu_traffic.sh writes
+    # profiles/traffic_r02.json with the library's SHA-1); a capture of another build is not reported
+    traffic, traffic_src = None, "no ncu capture of this build (profiles/traffic_r02.json absent or of another libh264b2.so)"
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        per_pic = tr.get({"inter": "k_inter", "intra": "k_intra", "deblock": "k_deblock"}[dom], {}).get("dram_bytes_per_picture")
-        traffic = int(per_pic * S) if per_pic else None      # per launch = per picture x pictures per launch
+        import hashlib
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
+        lib_sha = hashlib.sha1(open(engine.library_path(), "rb").read()).hexdigest()
+        if tr.get("lib_sha1") == lib_sha:
+            per_pic = tr.get({"inter": "k_inter", "intra": "k_intra", "deblock": "k_deblock"}[dom], {}).get("dram_bytes_per_picture")
+            traffic = int(per_pic * S) if per_pic else None      # per launch = per picture x pictures per launch
+            traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum of this build (profiles/traffic_r02.json), per launch of %d pictures" % S
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": {"inter": "k_inter", "intra": "k_intra", "deblock": "k_bs+k_deblock"}[dom], "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "share_of_step": round(dom_ms / ms_serial, 3), "kernels": kernels,
                 "timing": "CUDA events around every launch on its stream, one extra step with the look-ahead stream off (kernels serialised): %.1f ms; the timed steps overlap k_residual/k_bs of batch i+1 with the wavefront kernels of batch i: %.1f ms per step" % (ms_serial, ms / args.steps)}
     kernels["residual"] = {"ms_per_step": round(kt["residual"]["ms"] / kt_steps, 3), "launches_per_step": kt["residual"]["launches"] // kt_steps}
@@ -424,8 +480,47 @@ def main():
         out_host = [eng.pinned_array(S * eng.frame_bytes) for _ in range(nbuf)]
         out_ptrs = [[int(o.ctypes.data) + s * eng.frame_bytes for s in sids] for o in out_host]
 
+        # Host packing INSIDE the timed region: the host stage packs the levels and motion records of every (stream, picture) it
+        # submits (h264b2_pack_coefs / h264b2_pack_motion).  The replicas share one page-locked copy of each packed picture, so the
+        # work is done for real — S x pictures pack calls per step on a pool of host threads, one batch ahead of its submit — and
+        # its output goes to per-thread scratch buffers (the bytes are identical to the shared copy the DMA reads).
+        pack_pool, pack_futs, n_pack_threads = None, {}, 0
+        if not args.dense_coefs and not args.no_pack_in_e2e:
+            from concurrent.futures import ThreadPoolExecutor
+            n_pack_threads = max(1, usable_cores() // world - 1)
+            pack_pool = ThreadPoolExecutor(max_workers=n_pack_threads)
+            scratch = {}
+
+            def pack_range(i, lo, hi):
+                import threading as _th
+                tid = _th.get_ident()
+                for s_ in range(lo, hi):
+                    v = variants[var_of[s_]]
+                    pic = v["rp"].pictures[pic_of(s_, i)]
+                    cbn = int(eng.lib.h264b2_pack_coefs_bound(len(pic.coefs)))
+                    mbn = int(eng.lib.h264b2_pack_coefs_bound(pic.motion.size * 76)) if pic.motion is not None and pic.has_inter else 0
+                    buf = scratch.get(tid)
+                    if buf is None or buf.size < cbn + mbn + 64:
+                        raw_ = np.empty(max(cbn + mbn + 64, 8 << 20), np.uint8)
+                        buf = scratch[tid] = raw_[(-raw_.ctypes.data) % 16:]
+                    engine.pack_coefs(pic.coefs, buf[:cbn])
+                    if mbn:
+                        o_ = (cbn + 15) & ~15
+                        engine.pack_motion(pic.motion, buf[o_:o_ + mbn])
+
+            def pack_batch(i):
+                per = (S + n_pack_threads - 1) // n_pack_threads
+                return [pack_pool.submit(pack_range, i, lo, min(S, lo + per)) for lo in range(0, S, per)]
+
         def e2e_step():
+            if pack_pool is not None:
+                pack_futs[0] = pack_batch(0)
             for i, b in enumerate(host_batches):
+                if pack_pool is not None:
+                    if i + 1 < npic:
+                        pack_futs[i + 1] = pack_batch(i + 1)
+                    for f_ in pack_futs.pop(i):
+                        f_.result()
                 if args.e2e_mode == "d2h":
                     eng.submit_prepared(batches[i])
                 else:
@@ -453,7 +548,9 @@ def main():
         e2e = {"value": round(S * npic * args.e2e_steps * world / t1, 1), "unit": UNIT,
                "h2d_bytes_per_step": int(sum(variants[var_of[s]]["host_bytes"][pic_of(s, i)] for s in sids for i in range(npic))),
                "host_pack_ms_per_picture": None if args.dense_coefs else round(max(v["pack_ms"] for v in variants), 3),
-               "host_pack_note": "h264b2_pack_coefs + h264b2_pack_motion on one host core, done once per picture by the host stage BEFORE the timed region (the timed region starts at the C-ABI call)",
+               "host_pack_in_timed_region": pack_pool is not None, "host_pack_threads": n_pack_threads,
+               "host_pack_note": ("h264b2_pack_coefs + h264b2_pack_motion run INSIDE the timed region for every (stream, picture) of every step, on %d host threads, one batch ahead of its submit" % n_pack_threads) if pack_pool is not None
+                                 else "h264b2_pack_coefs + h264b2_pack_motion done once per picture BEFORE the timed region (the timed region starts at the C-ABI call)",
                "host_layout": host_layout, "arrays": "plain (dense int16 levels, 152-byte motion records)" if args.dense_coefs else "packed levels and motion records (h264b2_pack_coefs / h264b2_pack_motion)",
                "d2h_bytes_per_step": int(npic * S * eng.frame_bytes),
                "steps": args.e2e_steps, "device_ms_per_step": round(e2e_dev_ms / args.e2e_steps, 1),
@@ -465,6 +562,9 @@ def main():
     stream_files = [os.path.join(REF_DIR, "streams", st + ".h264") for st in stems]
     if not args.no_bitstream and all(os.path.exists(f) for f in stream_files):
         from h264_video_decoder_demo_b200 import frontend
+        for r_ in rs:
+            r_.free()
+        rs = []
         eng.close()
         nstr = args.bitstream_streams
         threads = args.bitstream_threads or max(1, usable_cores() // world)
@@ -482,6 +582,26 @@ def main():
                     "h2d_bytes": st_b["h2d_bytes"], "d2h_bytes": st_b["d2h_bytes"], "submits": st_b["submits"],
                     "checked": "every stream's output-order checksum chain equals the reference decoder's" if hashes_want is not None else "not checked (prefix fixtures)",
                     "what": "h264b2_multi_decode: Annex-B byte streams in, every output picture in page-locked host memory; host entropy decoding + derivations included"}
+
+    # ---- the other BASELINE.json configurations, shortly (device-resident replay, parity-checked): config 3 (field/MBAFF stream), config 4
+    #      (the long-GOP stream; it has ONE closed GOP, so GOP-parallelism is shown on the two-GOP HeavyHand stream by the tests and the
+    #      multi-stream pipeline), config 5 (64 streams of all five variants, STRONG scaling: 64 / N streams per GPU)
+    configs = None
+    if not args.no_configs and args.workload == "B_frames.cabac" and args.max_pictures is None:
+        try:
+            for r_ in rs:
+                r_.free()
+            rs = []
+            eng.close()
+        except Exception:
+            pass
+        configs = {}
+        configs["tff_mbaff"] = dict(measure_config("tff", [WORKLOADS["tff"]], S, local_rank, world), baseline_config=3, scaling="weak")
+        configs["gop121_long_gop"] = dict(measure_config("gop121", [WORKLOADS["gop121"]], S, local_rank, world), baseline_config=4, scaling="weak",
+                                          note="one closed GOP (single IDR): replicas only; closed-GOP splitting is exercised on the HeavyHand streams (tests, H264B2_MULTI_SPLIT_GOPS)")
+        per_gpu = max(1, 64 // world)
+        configs["mixed_64_streams"] = dict(measure_config("mixed", [WORKLOADS[w] for w in MIXED], per_gpu, local_rank, world), baseline_config=5, scaling="strong",
+                                           note="64 streams in total, all five bundled variants round-robin, 64 / n_gpus per GPU")
 
     # ---- CPU baseline: the unmodified reference on one host core (rank 0, N=1 only)
     cpu = None
@@ -504,7 +624,10 @@ def main():
                        "pictures_per_step_per_gpu": S * npic, "streams_per_gpu": S, "picture": "1920x1088 I420",
                        "l2": "inputs larger than L2: one distinct SoA copy + 17-surface DPB per stream (%.1f GB per GPU)" % l2_gb,
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_bitstream": e2e_bits, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_bitstream": e2e_bits,
+            # the ratio-ready whole-decoder number (Annex-B in, frames out, host entropy decoding included): like for like with the reference arm
+            "e2e_whole_decoder": ({"value": e2e_bits["value"], "unit": UNIT, "what": "h264b2_multi_decode (Annex-B byte streams in, frames in host memory out); compare THIS with the reference arm, which decodes from the bitstream too"} if e2e_bits else None),
+            "configs": configs, "gpu_launches": launches, "clocks": clocks,
         }) + "\n").encode())
     if world > 1:
         import torch.distributed as dist

@@ -421,11 +421,16 @@ int Front::mark_reference() {
                 for (int k = 0; k < 16; k++) if (slots[k].mark == MARK_LONG && slots[k].LongTermFrameIdx > maxidx) unmark(slots[k]);
                 c.MaxLongTermFrameIdx = maxidx;
             } else if (m.op == 5) {
-                for (int k = 0; k < 16; k++) if (k != cur && (slots[k].mark == MARK_SHORT || slots[k].mark == MARK_LONG)) unmark(slots[k]);
+                // RPL:2037-2045: EVERY entry of the DPB loses its frame-level and parent-level marks and its marked coded type, whatever it
+                // held (the current picture gets its short-term mark back below)
+                for (int k = 0; k < 16; k++) { slots[k].mark = MARK_UNUSED; slots[k].p_mark = MARK_UNUSED; slots[k].p_coded_marked = 0; }
                 c.MaxLongTermFrameIdx = -1; c.mmco5 = 1;
             } else if (m.op == 6) {
-                for (int k = 0; k < 16; k++) if (slots[k].mark == MARK_LONG && slots[k].LongTermFrameIdx == m.long_term_frame_idx) unmark(slots[k]);
-                c.mark = MARK_LONG; c.p_mark = MARK_LONG; c.p_coded_marked = 1; c.LongTermFrameIdx = m.long_term_frame_idx; c.mmco6 = 1;
+                // RPL:2062: the reference looks for the frame that already holds this index with max_long_term_frame_idx_plus1 - 1 of the
+                // SAME entry, which an operation 6 never carries (the entry is zeroed, so it compares with -1): nothing is ever released here
+                // RPL:2097-2099: for a frame only the FRAME-level mark becomes long-term; the parent-level mark and its coded type are set
+                // in the field branches alone, so the parent keeps what it had (that is what the slot choice and the IDR wipe look at)
+                c.mark = MARK_LONG; c.LongTermFrameIdx = m.long_term_frame_idx; c.mmco6 = 1;
             }
         }
     }

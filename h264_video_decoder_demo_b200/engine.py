@@ -58,6 +58,11 @@ class EngineError(RuntimeError):
     pass
 
 
+def library_path() -> str:
+    """The engine library this process loads (H264B2_LIB overrides the in-tree build for A/B runs)."""
+    return os.environ.get("H264B2_LIB", _build.LIB)
+
+
 def load_library(build_if_missing: bool = True) -> C.CDLL:
     """Load libh264b2.so (building it first when absent).  Needs no GPU: only symbol resolution."""
     global _LIB

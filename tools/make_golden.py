@@ -48,7 +48,15 @@ SYNTH = [("synth_cavlc_ip", dict(seed=11, n_pics=5)),
          ("synth_b_direct", dict(seed=15, bframes=True, n_pics=7)),
          ("synth_b_implicit", dict(seed=16, bframes=True, bipred_idc=2, n_pics=7, n_refs=4)),
          ("synth_b_explicit_t8x8", dict(seed=17, bframes=True, bipred_idc=1, weighted=True, n_pics=7, t8x8=True)),
-         ("synth_b_explicit_6x5", dict(seed=18, bframes=True, bipred_idc=1, wmb=6, hmb=5, n_pics=9, max_slices=1))]
+         ("synth_b_explicit_6x5", dict(seed=18, bframes=True, bipred_idc=1, wmb=6, hmb=5, n_pics=9, max_slices=1)),
+         # adaptive reference marking, long-term reference pictures, list modification with long-term picture numbers.
+         # What the UNMODIFIED reference decodes: MMCO 1, 2, 3, 5, 6, IDR long_term_reference_flag, modification_of_pic_nums_idc 0/1/2.
+         # MMCO 4 (max_long_term_frame_idx) makes the reference crash or lose its reference lists (tests/test_front_end.py records it).
+         ("synth_mmco1_mod", dict(seed=301, mmco=True, mmco_set=(1,), mmco_idr_lt=False, n_pics=8, n_refs=4, max_slices=2)),
+         ("synth_mmco_lt_idr", dict(seed=315, mmco=True, mmco_set=(1, 2), n_pics=8, n_refs=4, max_slices=2)),
+         ("synth_mmco_lt_36", dict(seed=331, mmco=True, mmco_set=(1, 2, 3, 6), n_pics=9, n_refs=4, max_slices=2)),
+         ("synth_mmco_lt_poc0_wp", dict(seed=300, mmco=True, mmco_set=(1, 2, 3, 6), poc_type=0, weighted=True, t8x8=True, n_pics=8, n_refs=4, max_slices=2)),
+         ("synth_mmco5_poc0", dict(seed=301, mmco=True, mmco_set=(1,), mmco_idr_lt=False, mmco5=True, poc_type=0, n_pics=9, n_refs=4, max_slices=2))]
 
 
 def make_synthetic(out_dir):
@@ -62,7 +70,10 @@ def make_synthetic(out_dir):
     import tempfile
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import h264_writer
+    only = os.environ.get("GOLDEN_ONLY")            # e.g. GOLDEN_ONLY=synth_mmco: regenerate just those fixtures
     for name, cfg in SYNTH:
+        if only and not name.startswith(only):
+            continue
         data = h264_writer.Stream(**cfg).build()
         n = cfg["n_pics"]
         with open(os.path.join(out_dir, f"{name}.first{n}.h264"), "wb") as f:
