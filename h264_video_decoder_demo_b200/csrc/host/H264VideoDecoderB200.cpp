@@ -146,11 +146,12 @@ int CH264VideoDecoderB200::open_bitstream(const char *url) {
     std::deque<void *> inflight;       // picture blocks whose DMA may still be pending (h264b2_submit keeps 3 batches in flight)
     int wmb = 0, hmb = 0, n_frames = 0;
     H264B2FrontEvent ev;
+    H264B2StreamInfo sinfo; memset(&sinfo, 0, sizeof sinfo);
     // picture size: parse up to the first picture with a throw-away front end (the context needs the size up front)
     if (h264b2_front_create(&probe, nullptr, nullptr, nullptr) || h264b2_front_open_file(probe, url)) FAIL(-1, "open: %s", probe ? h264b2_front_last_error(probe) : "out of memory");
     for (;;) {
         if (h264b2_front_next(probe, &ev) < 0) FAIL(-1, "open: %s", h264b2_front_last_error(probe));
-        if (ev.kind == H264B2_EV_PICTURE) { wmb = ev.width_mbs; hmb = ev.height_mbs; break; }
+        if (ev.kind == H264B2_EV_PICTURE) { wmb = ev.width_mbs; hmb = ev.height_mbs; h264b2_front_stream_info(probe, &sinfo); break; }
         if (ev.kind == H264B2_EV_END) FAIL(-1, "open: %s holds no decodable picture", url);
     }
     h264b2_front_destroy(probe); probe = nullptr;
@@ -187,6 +188,7 @@ int CH264VideoDecoderB200::open_bitstream(const char *url) {
                 b.m_pic_buff_luma = frame; b.m_pic_buff_cb = frame + (size_t)W * H; b.m_pic_buff_cr = b.m_pic_buff_cb + (size_t)(W / 2) * (H / 2);
                 b.PicWidthInSamplesL = W; b.PicHeightInSamplesL = H; b.PicWidthInSamplesC = W / 2; b.PicHeightInSamplesC = H / 2;
                 b.PicOrderCnt = surf_poc[ev.surface]; b.m_PicNumCnt = surf_idx[ev.surface]; b.slice_type = surf_type[ev.surface]; b.MbaffFrameFlag = surf_mbaff[ev.surface];
+                b.profile_idc = sinfo.profile_idc; b.level_idc = sinfo.level_idc; b.entropy_coding_mode_flag = sinfo.entropy_coding_mode_flag; b.fps = (float)sinfo.fps;
                 n_frames++;
                 if (m_output_frame_callback && m_output_frame_callback(&out, m_userData, H264_DECODE_ERROR_CODE_NO) != 0) break;      // VD:119-124: stop
             } else { ended = true; break; }

@@ -583,6 +583,18 @@ extern "C" int h264b2_front_open_file(H264B2Front *f, const char *path) {
 }
 extern "C" int h264b2_front_next(H264B2Front *f, H264B2FrontEvent *ev) { if (!f || !ev) return -1; return f->f.next_event(ev); }
 extern "C" int h264b2_front_release(H264B2Front *f, void *block) { if (!f) return -1; if (block) f->f.release_block(block); return 0; }
+extern "C" int h264b2_front_stream_info(H264B2Front *f, H264B2StreamInfo *info) {
+    if (!f || !info) return -1;
+    const h264b2::SPS &sps = f->f.pic_sh.sps; const h264b2::PPS &pps = f->f.pic_sh.pps;
+    if (!sps.valid) return -1;
+    info->profile_idc = sps.profile_idc; info->level_idc = sps.level_idc; info->entropy_coding_mode_flag = pps.entropy_coding_mode_flag;
+    info->frame_mbs_only_flag = sps.frame_mbs_only_flag; info->mb_adaptive_frame_field_flag = sps.mb_adaptive_frame_field_flag;
+    info->width_mbs = sps.PicWidthInMbs; info->height_mbs = sps.FrameHeightInMbs; info->max_num_ref_frames = sps.max_num_ref_frames;
+    info->transform_8x8_mode_flag = pps.transform_8x8_mode_flag;
+    info->fps = 25.0;
+    if (sps.timing_info_present_flag && sps.num_units_in_tick) info->fps = 1.0 * sps.time_scale / sps.num_units_in_tick / 2.0;      // H264SPS.cpp:346-356
+    return 0;
+}
 extern "C" const char *h264b2_front_last_error(H264B2Front *f) { return f ? f->f.error.c_str() : "null front end"; }
 
 extern "C" int h264b2_front_write_container(const char *h264_path, const char *container_path, int max_pictures) {

@@ -71,6 +71,7 @@ struct SPS {
     int max_num_ref_frames = 0, gaps_in_frame_num_value_allowed_flag = 0, pic_width_in_mbs_minus1 = 0, pic_height_in_map_units_minus1 = 0;
     int frame_mbs_only_flag = 1, mb_adaptive_frame_field_flag = 0, direct_8x8_inference_flag = 0;
     int max_num_reorder_frames = -1;
+    int timing_info_present_flag = 0; uint32_t num_units_in_tick = 0, time_scale = 0;      // VUI timing (the reference derives its `fps` from it)
     // derived
     int PicWidthInMbs = 0, PicHeightInMapUnits = 0, FrameHeightInMbs = 0, ChromaArrayType = 1, MaxFrameNum = 16, MaxPicOrderCntLsb = 16, ExpectedDeltaPerPicOrderCntCycle = 0;
     SPS() { memset(ScalingList4x4, 0, sizeof ScalingList4x4); memset(ScalingList8x8, 0, sizeof ScalingList8x8); memset(offset_for_ref_frame, 0, sizeof offset_for_ref_frame); }

@@ -65,7 +65,7 @@ int parse_sps(BitReader &br, SPS &s) {
         if (br.u1()) br.u1();
         if (br.u1()) { br.u(3); br.u1(); if (br.u1()) { br.u(8); br.u(8); br.u(8); } }
         if (br.u1()) { br.ue(); br.ue(); }
-        if (br.u1()) { br.u(32); br.u(32); br.u1(); }
+        if (br.u1()) { s.timing_info_present_flag = 1; s.num_units_in_tick = br.u(32); s.time_scale = br.u(32); br.u1(); }
         const int nal_hrd = br.u1(); if (nal_hrd) hrd_parameters(br);
         const int vcl_hrd = br.u1(); if (vcl_hrd) hrd_parameters(br);
         if (nal_hrd || vcl_hrd) br.u1();

@@ -21,7 +21,8 @@ H264_DECODE_ERROR_CODE_FILE_END = 1
 class _PicBase(C.Structure):
     _fields_ = [("m_pic_buff_luma", C.POINTER(C.c_uint8)), ("m_pic_buff_cb", C.POINTER(C.c_uint8)), ("m_pic_buff_cr", C.POINTER(C.c_uint8)),
                 ("PicWidthInSamplesL", C.c_int32), ("PicHeightInSamplesL", C.c_int32), ("PicWidthInSamplesC", C.c_int32), ("PicHeightInSamplesC", C.c_int32),
-                ("PicOrderCnt", C.c_int32), ("m_PicNumCnt", C.c_int32), ("slice_type", C.c_int32), ("MbaffFrameFlag", C.c_int32)]
+                ("PicOrderCnt", C.c_int32), ("m_PicNumCnt", C.c_int32), ("slice_type", C.c_int32), ("MbaffFrameFlag", C.c_int32),
+                ("profile_idc", C.c_int32), ("level_idc", C.c_int32), ("entropy_coding_mode_flag", C.c_int32), ("fps", C.c_float)]
 
 
 class _Pic(C.Structure):

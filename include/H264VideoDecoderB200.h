@@ -25,6 +25,10 @@ struct CH264PictureBaseB200 {          /* the fields consumers of the reference 
     uint8_t *m_pic_buff_luma, *m_pic_buff_cb, *m_pic_buff_cr;
     int32_t PicWidthInSamplesL, PicHeightInSamplesL, PicWidthInSamplesC, PicHeightInSamplesC;
     int32_t PicOrderCnt, m_PicNumCnt, slice_type, MbaffFrameFlag;
+    /* m_h264_slice_header.m_sps / m_pps fields the reference's player reads (SDH264Player/MyStatic.cpp:190-211); Annex-B input only,
+     * 0 for pre-parsed containers (they do not carry parameter sets) */
+    int32_t profile_idc, level_idc, entropy_coding_mode_flag;
+    float fps;
 };
 struct CH264PictureB200 { CH264PictureBaseB200 m_picture_frame; };
 

@@ -66,6 +66,15 @@ int h264b2_front_gop_offsets(const uint8_t *data, size_t bytes, size_t *offsets,
  * parsed first.  more_follows = 1: the last picture of the range is completed the way the reference completes a picture that
  * is followed by another one (deblocked, H264PictureBase.cpp:707) instead of as the stream's tail picture (Q1). */
 int h264b2_front_open_range(H264B2Front *f, const uint8_t *data, size_t bytes, size_t begin, size_t end, int more_follows);
+/* Stream-level facts the reference keeps in the picture's slice header copy (CH264PictureBase::m_h264_slice_header.m_sps / m_pps) and its
+ * second consumer reads (SDH264Player/MyStatic.cpp:190-211): valid after the first H264B2_EV_PICTURE.  fps as H264SPS.cpp:346-356
+ * derives it (25 without VUI timing, else time_scale / num_units_in_tick / 2). */
+typedef struct H264B2StreamInfo {
+    int32_t profile_idc, level_idc, entropy_coding_mode_flag, frame_mbs_only_flag, mb_adaptive_frame_field_flag;
+    int32_t width_mbs, height_mbs, max_num_ref_frames, transform_8x8_mode_flag;
+    double fps;
+} H264B2StreamInfo;
+int h264b2_front_stream_info(H264B2Front *f, H264B2StreamInfo *info);
 /* Pull the next event. Returns 0, or <0 on a fatal stream error (message in h264b2_front_last_error). */
 int h264b2_front_next(H264B2Front *f, H264B2FrontEvent *ev);
 /* Give a picture block back for reuse (blocks still out at destroy time are freed there). */
