@@ -225,7 +225,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--streams", type=int, default=128, help="concurrent replicas of the stream per GPU")
+    ap.add_argument("--streams", type=int, default=0, help="concurrent replicas of the stream per GPU (0 = 256, halved until the replicas fit in HBM)")
     ap.add_argument("--workload", default="B_frames.cabac", choices=sorted(WORKLOADS) + ["mixed"],
                     help="one bundled stream replicated S times, or 'mixed' = all five bundled variants dealt round-robin over the S streams")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -271,78 +271,96 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    S = args.streams
+    S = args.streams or 256
     eng_probe = engine.load_library()   # fails loudly when the CUDA library is missing: no fallback
     del eng_probe
-    # one variant per distinct bitstream: page-locked copy of its container (the e2e leg DMAs every picture's arrays
-    # straight from it) + replicas resident in HBM, one distinct copy of the SoA per stream
-    variants, is_full, eng = [], True, None
-    for st in stems:
-        path, full = find_replay(st)
-        is_full &= full
-        raw = replay.read_replay_bytes(path)
-        if eng is None:
-            rp0 = replay.parse_replay(raw, path, 1)
-            eng = engine.Engine(local_rank, S, rp0.width_mbs, rp0.height_mbs)
-        pinned = eng.pinned_array(len(raw))
-        pinned[:] = np.frombuffer(raw, dtype=np.uint8)
-        del raw
-        rpv = replay.parse_replay(pinned, path, args.max_pictures)
-        # what the host stage hands to h264b2_submit: one page-locked block per picture (the layout of the front end's picture
-        # blocks: arrays back to back, 64-byte aligned -> ONE DMA per picture), coefficients packed by h264b2_pack_coefs
-        blobs, host_params = None, None
-        if not args.dense_coefs:
-            names = ("mb_info", "intra_modes", "coef_offset", "motion", "weights", "level_scale4", "level_scale8")
-            al = lambda n: (n + 63) & ~63
-            cb = lambda pic: int(eng.lib.h264b2_pack_coefs_bound(len(pic.coefs)))
-            mb_ = lambda pic: int(eng.lib.h264b2_pack_coefs_bound(pic.motion.size * 76)) if pic.motion is not None else 0
-            bound = sum(sum(al(getattr(pic, k).nbytes) for k in names if getattr(pic, k) is not None) + al(cb(pic)) + al(mb_(pic)) + 64 for pic in rpv.pictures)
-            store, blobs, mblobs, host_params, o = eng.pinned_array(bound), [], [], [], 0
-            o += (-store.ctypes.data) % 64
-            extents = []
-            t_pack = 0.0
-            for pic in rpv.pictures:
-                ptrs, o0, mblob = {}, o, None
-                for k in names:
-                    a = getattr(pic, k)
-                    if a is None or not a.size:
-                        continue
-                    if k == "motion":
-                        if not pic.has_inter:
-                            continue
+    rs, eng = [], None
+    while True:
+        try:
+            # one variant per distinct bitstream: page-locked copy of its container (the e2e leg DMAs every picture's arrays
+            # straight from it) + replicas resident in HBM, one distinct copy of the SoA per stream
+            variants, is_full, eng = [], True, None
+            for st in stems:
+                path, full = find_replay(st)
+                is_full &= full
+                raw = replay.read_replay_bytes(path)
+                if eng is None:
+                    rp0 = replay.parse_replay(raw, path, 1)
+                    eng = engine.Engine(local_rank, S, rp0.width_mbs, rp0.height_mbs)
+                pinned = eng.pinned_array(len(raw))
+                pinned[:] = np.frombuffer(raw, dtype=np.uint8)
+                del raw
+                rpv = replay.parse_replay(pinned, path, args.max_pictures)
+                # what the host stage hands to h264b2_submit: one page-locked block per picture (the layout of the front end's picture
+                # blocks: arrays back to back, 64-byte aligned -> ONE DMA per picture), coefficients packed by h264b2_pack_coefs
+                blobs, host_params = None, None
+                if not args.dense_coefs:
+                    names = ("mb_info", "intra_modes", "coef_offset", "motion", "weights", "level_scale4", "level_scale8")
+                    al = lambda n: (n + 63) & ~63
+                    cb = lambda pic: int(eng.lib.h264b2_pack_coefs_bound(len(pic.coefs)))
+                    mb_ = lambda pic: int(eng.lib.h264b2_pack_coefs_bound(pic.motion.size * 76)) if pic.motion is not None else 0
+                    bound = sum(sum(al(getattr(pic, k).nbytes) for k in names if getattr(pic, k) is not None) + al(cb(pic)) + al(mb_(pic)) + 64 for pic in rpv.pictures)
+                    store, blobs, mblobs, host_params, o = eng.pinned_array(bound), [], [], [], 0
+                    o += (-store.ctypes.data) % 64
+                    extents = []
+                    t_pack = 0.0
+                    for pic in rpv.pictures:
+                        ptrs, o0, mblob = {}, o, None
+                        for k in names:
+                            a = getattr(pic, k)
+                            if a is None or not a.size:
+                                continue
+                            if k == "motion":
+                                if not pic.has_inter:
+                                    continue
+                                t0p = time.perf_counter()
+                                mblob = engine.pack_motion(a, store[o:o + mb_(pic)])
+                                t_pack += time.perf_counter() - t0p
+                                ptrs[k] = mblob.ctypes.data
+                                o += al(mblob.size)
+                                continue
+                            store[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+                            ptrs[k] = store.ctypes.data + o
+                            o += al(a.nbytes)
                         t0p = time.perf_counter()
-                        mblob = engine.pack_motion(a, store[o:o + mb_(pic)])
+                        b = engine.pack_coefs(pic.coefs, store[o:o + cb(pic)])
                         t_pack += time.perf_counter() - t0p
-                        ptrs[k] = mblob.ctypes.data
-                        o += al(mblob.size)
-                        continue
-                    store[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
-                    ptrs[k] = store.ctypes.data + o
-                    o += al(a.nbytes)
-                t0p = time.perf_counter()
-                b = engine.pack_coefs(pic.coefs, store[o:o + cb(pic)])
-                t_pack += time.perf_counter() - t0p
-                o += al(b.size)
-                blobs.append(b)
-                mblobs.append(mblob)
-                ptrs["coefs"] = b.ctypes.data
-                host_params.append(replay.pic_params(rpv, pic, ptrs=ptrs, packed_blob=b, packed_motion=mblob))
-                extents.append((o0, o - o0, ptrs))
-        else:
-            host_params = [replay.pic_params(rpv, pic) for pic in rpv.pictures]
-        variants.append({"rp": rpv, "host_params": host_params, "_store": store if blobs else None, "extents": extents if blobs else None, "blobs": blobs, "mblobs": mblobs if blobs else None,
-                         "pack_ms": (1000.0 * t_pack / max(1, len(rpv.pictures))) if blobs else None,
-                         "host_bytes": [e[1] for e in extents] if blobs else [pic.nbytes() for pic in rpv.pictures], "rs": None})
-    sids = list(range(S))
-    var_of = [s % len(variants) for s in sids]
-    rs = []
-    for s in sids:
-        v = variants[var_of[s]]
-        if v["rs"] is None:
-            v["rs"] = engine.ResidentStream(eng, v["rp"])
-            rs.append(v["rs"])
-        else:
-            rs.append(v["rs"].clone())
+                        o += al(b.size)
+                        blobs.append(b)
+                        mblobs.append(mblob)
+                        ptrs["coefs"] = b.ctypes.data
+                        host_params.append(replay.pic_params(rpv, pic, ptrs=ptrs, packed_blob=b, packed_motion=mblob))
+                        extents.append((o0, o - o0, ptrs))
+                else:
+                    host_params = [replay.pic_params(rpv, pic) for pic in rpv.pictures]
+                variants.append({"rp": rpv, "host_params": host_params, "_store": store if blobs else None, "extents": extents if blobs else None, "blobs": blobs, "mblobs": mblobs if blobs else None,
+                                 "pack_ms": (1000.0 * t_pack / max(1, len(rpv.pictures))) if blobs else None,
+                                 "host_bytes": [e[1] for e in extents] if blobs else [pic.nbytes() for pic in rpv.pictures], "rs": None})
+            sids = list(range(S))
+            var_of = [s % len(variants) for s in sids]
+            rs = []
+            for s in sids:
+                v = variants[var_of[s]]
+                if v["rs"] is None:
+                    v["rs"] = engine.ResidentStream(eng, v["rp"])
+                    rs.append(v["rs"])
+                else:
+                    rs.append(v["rs"].clone())
+
+            break
+        except engine.EngineError as ex:
+            # the replicas (one distinct SoA copy + a 17-surface DPB per stream) did not fit: halve the stream count (only when it was not given)
+            if args.streams or S <= 32 or "memory" not in str(ex).lower():
+                raise
+            sys.stderr.write(f"bench: {S} streams do not fit in device memory ({ex}); retrying with {S // 2}\n")
+            try:
+                for r_ in rs:
+                    r_.free()
+                if eng is not None:
+                    eng.close()
+            except Exception:
+                pass
+            S //= 2
     rp = variants[0]["rp"]
     npic = max(len(v["rp"].pictures) for v in variants)          # submits per step; shorter streams wrap to their IDR
 
@@ -596,8 +614,8 @@ def main():
         except Exception:
             pass
         configs = {}
-        configs["tff_mbaff"] = dict(measure_config("tff", [WORKLOADS["tff"]], S, local_rank, world), baseline_config=3, scaling="weak")
-        configs["gop121_long_gop"] = dict(measure_config("gop121", [WORKLOADS["gop121"]], S, local_rank, world), baseline_config=4, scaling="weak",
+        configs["tff_mbaff"] = dict(measure_config("tff", [WORKLOADS["tff"]], min(S, 128), local_rank, world), baseline_config=3, scaling="weak")
+        configs["gop121_long_gop"] = dict(measure_config("gop121", [WORKLOADS["gop121"]], min(S, 128), local_rank, world), baseline_config=4, scaling="weak",
                                           note="one closed GOP (single IDR): replicas only; closed-GOP splitting is exercised on the HeavyHand streams (tests, H264B2_MULTI_SPLIT_GOPS)")
         per_gpu = max(1, 64 // world)
         configs["mixed_64_streams"] = dict(measure_config("mixed", [WORKLOADS[w] for w in MIXED], per_gpu, local_rank, world), baseline_config=5, scaling="strong",

@@ -34,7 +34,7 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v) {
 // counter stays the source of truth: the waiter re-reads it after every wake-up (mbarrier.try_wait also returns after a
 // hardware time limit, so a stale phase guess costs a delay, never a hang).
 #ifndef WF_PARK_NS
-#define WF_PARK_NS 0
+#define WF_PARK_NS 1000
 #endif
 #ifndef WF_MBAR
 #define WF_MBAR 1
@@ -48,9 +48,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ int mbar_try_wait(uint32_t bar, int parity) {
     int ok;
-    // optional suspend-time hint (WF_PARK_NS > 0).  Measured on B200 (round 2): without a hint the wait comes back after ~70 ns whether
-    // or not the phase completed, so the loop around it polls; with a 20 us hint the warp really parks, but wakes up so late after the
-    // arrival that the wavefront's critical path grew by 30 % (single-bundle latency 84 -> 108 ms per 75 pictures).  Default: no hint.
+    // suspend-time hint (WF_PARK_NS > 0).  Measured on B200 (round 2): without a hint the wait comes back after ~70 ns whether or not the
+    // phase completed, so the loop around it polls — ncu counted as many warp instructions in that loop as in the filters (k_deblock3) and
+    // 42 M loop trips per k_intra launch.  With a hint the warp stays parked until the arrival or the time limit; kernel times are the same
+    // within noise (175.8 vs 175.7 ms per step), the issue slots go to the look-ahead stream's kernels instead of the poll.
     if (WF_PARK_NS > 0)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.s32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity), "r"(WF_PARK_NS) : "memory");
     else
