@@ -225,7 +225,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--streams", type=int, default=0, help="concurrent replicas of the stream per GPU (0 = 256, halved until the replicas fit in HBM)")
+    ap.add_argument("--streams", type=int, default=0, help="concurrent replicas of the stream per GPU (0 = 384, halved until the replicas fit in HBM)")
     ap.add_argument("--workload", default="B_frames.cabac", choices=sorted(WORKLOADS) + ["mixed"],
                     help="one bundled stream replicated S times, or 'mixed' = all five bundled variants dealt round-robin over the S streams")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -271,7 +271,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    S = args.streams or 256
+    S = args.streams or 384
     eng_probe = engine.load_library()   # fails loudly when the CUDA library is missing: no fallback
     del eng_probe
     rs, eng = [], None

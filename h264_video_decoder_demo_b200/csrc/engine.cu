@@ -184,7 +184,7 @@ struct H264B2Context {
     uint8_t *surfaces;
     uint32_t *bs;
     int16_t *res;
-    int *progress;            // [n_streams][2][hmb] then DESC_RING*2 tickets
+    int *progress;            // [n_streams][3][hmb] (intra / luma intra, deblock, chroma intra) then DESC_RING * 6 * MAX_GROUPS tickets
     size_t progress_ints;
     int16_t *ls_flat;         // ls4 [2][2][6][16] then ls8 [2][2][6][64]
     cudaStream_t st, st_h2d, st_h2d2, st_d2h;
@@ -217,6 +217,7 @@ struct H264B2Context {
     int *worklist; size_t worklist_stride;    // per stream: entry count + addresses of the macroblocks k_inter_tma leaves to k_inter_list
     int inter_tma; CUtensorMap map_y, map_c;   // TMA descriptors of the DPB (luma: x, y, surface; chroma: x, y, plane, surface); H264B2_INTER_V1=1 keeps the LDG kernel
     int debug_launch;                         // H264B2_DEBUG_LAUNCH=1: check for a launch error after every kernel of a batch
+    int intra_split; cudaStream_t st_chroma[MAX_GROUPS]; cudaEvent_t chroma_fork[MAX_GROUPS], chroma_join[MAX_GROUPS];   // H264B2_INTRA_SPLIT=0: one intra wavefront for luma and chroma
     int deblock_v1;                           // H264B2_DEBLOCK_V1=1: first-generation progressive deblocking kernels (A/B runs)
     int lookahead; unsigned batch_no; cudaStream_t st_pre; cudaEvent_t pre_done[DESC_RING], main_done[2];
     size_t bs_stride;                         // words per stream in bs
@@ -379,7 +380,7 @@ static int create_impl(H264B2Context *c, int device, int n_streams, int surfaces
     CK(cudaStreamCreateWithFlags(&c->st_pre, cudaStreamNonBlocking));
     for (int i = 0; i < DESC_RING; i++) CK(cudaEventCreateWithFlags(&c->pre_done[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->main_done[i], cudaEventDisableTiming));
-    c->progress_ints = (size_t)n_streams * 2 * height_mbs + DESC_RING * 4 * MAX_GROUPS;
+    c->progress_ints = (size_t)n_streams * 3 * height_mbs + DESC_RING * 6 * MAX_GROUPS;
     {
         const char *g = getenv("H264B2_GROUPS"), *gm = getenv("H264B2_GROUP_MIN");
         c->groups = g ? atoi(g) : 1;      // measured (S=128): 1 group 15.0k, 2 groups 14.0k, 4 groups 13.3k frames/s — the GPU is already issue-bound
@@ -397,7 +398,9 @@ static int create_impl(H264B2Context *c, int device, int n_streams, int surfaces
     { const char *e = getenv("H264B2_D2H_CHUNK_MB"); c->d2h_chunk = e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : 0; }      // 0 = adaptive, see h264b2_read_pictures_async
     { const char *e = getenv("H264B2_D2H_ZEROCOPY"); c->d2h_ctas = e ? atoi(e) : 0; c->d2h_zerocopy = c->d2h_ctas > 0; }
     { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&c->st_d2h, cudaStreamNonBlocking, c->d2h_zerocopy ? hi : lo)); }
+    { const char *e = getenv("H264B2_INTRA_SPLIT"); c->intra_split = !(e && atoi(e) == 0); }
     for (int i = 0; i < MAX_GROUPS; i++) {
+        CK(cudaStreamCreateWithFlags(&c->st_chroma[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->chroma_fork[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->chroma_join[i], cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&c->st_g[i], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->st_side[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->side_fork[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->side_join[i], cudaEventDisableTiming));
@@ -465,7 +468,7 @@ extern "C" int h264b2_destroy(H264B2Context *c) {
     free(c->ev);
     ev_destroy(c->t0); ev_destroy(c->t1);
     st_destroy(c->st); st_destroy(c->st_h2d); st_destroy(c->st_h2d2); st_destroy(c->st_d2h);
-    for (int i = 0; i < MAX_GROUPS; i++) { st_destroy(c->st_g[i]); st_destroy(c->st_side[i]); ev_destroy(c->join_ev[i]); ev_destroy(c->side_fork[i]); ev_destroy(c->side_join[i]); }
+    for (int i = 0; i < MAX_GROUPS; i++) { st_destroy(c->st_chroma[i]); ev_destroy(c->chroma_fork[i]); ev_destroy(c->chroma_join[i]); st_destroy(c->st_g[i]); st_destroy(c->st_side[i]); ev_destroy(c->join_ev[i]); ev_destroy(c->side_fork[i]); ev_destroy(c->side_join[i]); }
     ev_destroy(c->fork_ev);
     delete c;
     return 0;
@@ -533,7 +536,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         d.dst = (uint8_t *)d.stream_base + (size_t)p.dst_surface * c->frame_bytes;
         d.bs = c->bs + ((size_t)par * c->n_streams + sids[i]) * c->bs_stride;
         d.res = c->res + ((size_t)par * c->n_streams + sids[i]) * c->nmb * RES_MB_STRIDE;
-        d.progress = c->progress + (size_t)sids[i] * 2 * c->hmb;
+        d.progress = c->progress + (size_t)sids[i] * 3 * c->hmb;
         d.frame_bytes = c->frame_bytes; d.surf0 = sids[i] * c->spp; d.worklist = c->worklist + (size_t)sids[i] * c->worklist_stride;
         d.wmb = c->wmb; d.hmb = c->hmb; d.mbaff = p.mbaff_frame_flag; d.cqp0 = p.chroma_qp_offset[0]; d.cqp1 = p.chroma_qp_offset[1];
         d.deblock_enable = p.deblock_enable; d.deblock_stop = p.deblock_stop_mb < c->nmb ? p.deblock_stop_mb : c->nmb;
@@ -542,7 +545,7 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         n_prog += !d.generic;
         any_inter |= p.has_inter; any_deblock |= p.deblock_enable;
     }
-    int *tickets = c->progress + (c->progress_ints - DESC_RING * 4 * MAX_GROUPS) + ring * 4 * MAX_GROUPS;
+    int *tickets = c->progress + (c->progress_ints - DESC_RING * 6 * MAX_GROUPS) + ring * 6 * MAX_GROUPS;
     const bool la = c->lookahead != 0;
     cudaStream_t sp = la ? c->st_pre : c->st;
     if (la) {
@@ -623,24 +626,33 @@ static int launch_batch(H264B2Context *c, int n, const int32_t *sids, const H264
         }
         if (np) {
             class_begin(c, 2, sg);
-            k_intra<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g);
+            if (c->intra_split) {
+                // luma and chroma intra prediction as two independent wavefronts: side by side on two streams when the look-ahead schedule is
+                // on, one after the other when every kernel is timed alone
+                cudaStream_t sc = la ? c->st_chroma[g] : sg;
+                if (la) { CK(cudaEventRecord(c->chroma_fork[g], sg)); CK(cudaStreamWaitEvent(sc, c->chroma_fork[g], 0)); }
+                k_intra<false, 2><<<np * bands, WF_THREADS, 0, sc>>>(dg, np, bands, tickets + 6 * g + 4);
+                if (la) CK(cudaEventRecord(c->chroma_join[g], sc));
+                k_intra<false, 1><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 6 * g);
+                if (la) CK(cudaStreamWaitEvent(sg, c->chroma_join[g], 0));
+            } else k_intra<false, 3><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 6 * g);
             LCHK("k_intra<false>");
             class_end(c, 2, sg);
             if (g_deblock) {
                 class_begin(c, 4, sg);
-                if (c->deblock_v1) k_deblock<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 4 * g + 2);
-                else { const int bands3 = (c->hmb + DB3_ROWS - 1) / DB3_ROWS; k_deblock3<<<((np + DB_PPW - 1) / DB_PPW) * bands3, DB3_THREADS, 0, sg>>>(dg, np, bands3, tickets + 4 * g + 2); }
+                if (c->deblock_v1) k_deblock<false><<<np * bands, WF_THREADS, 0, sg>>>(dg, np, bands, tickets + 6 * g + 2);
+                else { const int bands3 = (c->hmb + DB3_ROWS - 1) / DB3_ROWS; k_deblock3<<<((np + DB_PPW - 1) / DB_PPW) * bands3, DB3_THREADS, 0, sg>>>(dg, np, bands3, tickets + 6 * g + 2); }
                 class_end(c, 4, sg);
             }
         }
         if (nq) {
             class_begin(c, 2, sq);
-            k_intra<true><<<nq * bands, WF_THREADS, 0, sq>>>(dg + np, nq, bands, tickets + 4 * g + 1);
+            k_intra<true><<<nq * bands, WF_THREADS, 0, sq>>>(dg + np, nq, bands, tickets + 6 * g + 1);
             LCHK("k_intra<true>");
             class_end(c, 2, sq);
             if (g_deblock) {
                 class_begin(c, 4, sq);
-                k_deblock<true><<<nq * bands, WF_THREADS, 0, sq>>>(dg + np, nq, bands, tickets + 4 * g + 3);
+                k_deblock<true><<<nq * bands, WF_THREADS, 0, sq>>>(dg + np, nq, bands, tickets + 6 * g + 3);
                 LCHK("k_deblock<true>");
                 class_end(c, 4, sq);
             }

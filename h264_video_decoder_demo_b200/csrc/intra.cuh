@@ -163,8 +163,12 @@ __device__ __forceinline__ void put_px(uint8_t *p, int have, int pred, int res) 
 // Reconstruct one intra (or I_PCM) macroblock with one warp.  FAST (progressive pictures): neighbour samples and
 // the MB itself live in a shared-memory tile for the whole MB (one L2 round trip in, one out); otherwise every
 // sample access goes through the generic MBAFF-aware neighbour derivation.
-template <bool FAST>
+// PLANES: 1 = luma only, 2 = Cb and Cr only, 3 = everything.  Luma and chroma prediction never read each other's samples, so progressive
+// pictures run them as two independent wavefronts (two launches of k_intra side by side): the luma chain loses the chroma work of
+// every macroblock, the chroma chain (one step per macroblock, neighbours A, B, D only) is short.
+template <bool FAST, int PLANES = 3>
 __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, int lane, IntraWarpSmem &S, const uint16_t *tab4, const uint16_t *tab8) {
+    constexpr bool LUMA = (PLANES & 1) != 0, CHROMA = (PLANES & 2) != 0;
     const int field = P.mbaff && (I.flags & H264B2_MBF_FIELD);
     const int ys = field ? 2 : 1;
     int x0, y0;
@@ -176,8 +180,8 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     if (cls == H264B2_MB_IPCM) {                                       // PB:2449
         if (!mb_coefs_in_bounds(P, a, H264B2_CM_PCM, cls, 0)) return;      // samples beyond the coefficient array: leave the buffer as it is
         const int16_t *pcm = P.coefs + P.coef_off[a];
-        for (int i = lane; i < 256; i += 32) Y[(size_t)(y0 + ys * (i >> 4)) * W + x0 + (i & 15)] = (uint8_t)pcm[i];
-        for (int i = lane; i < 64; i += 32) {
+        if (LUMA) for (int i = lane; i < 256; i += 32) Y[(size_t)(y0 + ys * (i >> 4)) * W + x0 + (i & 15)] = (uint8_t)pcm[i];
+        if (CHROMA) for (int i = lane; i < 64; i += 32) {
             Cb[(size_t)(yc0 + ys * (i >> 3)) * Wc + xc0 + (i & 7)] = (uint8_t)pcm[256 + i];
             Cr[(size_t)(yc0 + ys * (i >> 3)) * Wc + xc0 + (i & 7)] = (uint8_t)pcm[320 + i];
         }
@@ -198,18 +202,20 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
         avD = nD >= 0 && avail_addr(P, a, nD) && !(P.info[nD].flags & H264B2_MBF_CIP_UNAVAIL);
         // stage the tile: own samples (kept where a block is not predicted, Q15), the row above, the left column
         const uint8_t *Yp = Y + (size_t)y0 * W + x0;
+        if (LUMA) {
 #pragma unroll
-        for (int t = 0; t < 2; t++) { const int wd = lane + 32 * t, r = wd >> 2, j = wd & 3; S.Yt[1 + r][1 + j] = __ldcg((const uint32_t *)(Yp + (size_t)r * W + 4 * j)); }
-        { const int c = lane >> 4, cl = lane & 15, r = cl >> 1, j = cl & 1;
+            for (int t = 0; t < 2; t++) { const int wd = lane + 32 * t, r = wd >> 2, j = wd & 3; S.Yt[1 + r][1 + j] = __ldcg((const uint32_t *)(Yp + (size_t)r * W + 4 * j)); }
+        }
+        if (CHROMA) { const int c = lane >> 4, cl = lane & 15, r = cl >> 1, j = cl & 1;
           S.Ct[c][1 + r][1 + j] = __ldcg((const uint32_t *)((c ? Cr : Cb) + (size_t)(yc0 + r) * Wc + xc0 + 4 * j)); }
         if (y0 > 0) {
-            if (lane < 7) { if ((lane > 0 || x0 > 0) && (lane < 5 || x0 + 16 < W)) S.Yt[0][lane] = __ldcg((const uint32_t *)(Yp - W - 4 + 4 * lane)); }
+            if (lane < 7) { if (LUMA && (lane > 0 || x0 > 0) && (lane < 5 || x0 + 16 < W)) S.Yt[0][lane] = __ldcg((const uint32_t *)(Yp - W - 4 + 4 * lane)); }
             else if (lane >= 8 && lane < 14) { const int l = lane - 8, c = l / 3, j = l % 3;
-                if (j > 0 || x0 > 0) S.Ct[c][0][j] = __ldcg((const uint32_t *)((c ? Cr : Cb) + (size_t)(yc0 - 1) * Wc + xc0 - 4 + 4 * j)); }
+                if (CHROMA && (j > 0 || x0 > 0)) S.Ct[c][0][j] = __ldcg((const uint32_t *)((c ? Cr : Cb) + (size_t)(yc0 - 1) * Wc + xc0 - 4 + 4 * j)); }
         }
         if (x0 > 0) {
-            if (lane < 16) ((uint8_t *)S.Yt[1 + lane])[3] = __ldcg(Yp + (size_t)lane * W - 1);
-            else { const int l = lane - 16, c = l >> 3, r = l & 7; ((uint8_t *)S.Ct[c][1 + r])[3] = __ldcg((c ? Cr : Cb) + (size_t)(yc0 + r) * Wc + xc0 - 1); }
+            if (lane < 16) { if (LUMA) ((uint8_t *)S.Yt[1 + lane])[3] = __ldcg(Yp + (size_t)lane * W - 1); }
+            else if (CHROMA) { const int l = lane - 16, c = l >> 3, r = l & 7; ((uint8_t *)S.Ct[c][1 + r])[3] = __ldcg((c ? Cr : Cb) + (size_t)(yc0 + r) * Wc + xc0 - 1); }
         }
     }
     auto sample = [&](int xN, int yN, int comp) -> int {
@@ -232,6 +238,7 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
 #pragma unroll
         for (int t = 0; t < 6; t++) {
             const int w = lane + 32 * t, e = 2 * w, slot = e >> 4, inner = e & 15;
+            if (!(slot < 16 ? LUMA : CHROMA)) continue;
             const uint32_t v = hasres ? src[w] : 0u;
             int dsti;
             if (slot < 16) dsti = ((slot >> 2) * 4 + (inner >> 2)) * 16 + (slot & 3) * 4 + (inner & 3);
@@ -242,7 +249,8 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     }
     const int16_t *res = S.rt.res;
 
-    if (cls == H264B2_MB_I16x16) {                                      // PB:1847
+    if (!LUMA) { }
+    else if (cls == H264B2_MB_I16x16) {                                      // PB:1847
         const int mode = I.pred16_chroma & 3;
         const int nv = lane < 16 ? sample(lane, -1, 0) : sample(-1, lane - 16, 0);     // lanes 0-15 the row above, 16-31 the left column
         S.nb[1 + lane] = nv;
@@ -347,7 +355,7 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     }
 
     // chroma (PB:2076): the two components are independent, so lanes 0-15 predict Cb while lanes 16-31 predict Cr
-    {
+    if (CHROMA) {
         const int cmode = (I.pred16_chroma >> 2) & 3;
         const int comp = 1 + (lane >> 4), hl = lane & 15;
         int *nbc = S.nb + 17 * (lane >> 4);              // [0] corner, [1..8] top, [9..16] left
@@ -391,10 +399,14 @@ __device__ inline void intra_mb(const PicDev &P, int a, const H264B2MbInfo &I, i
     __syncwarp();
     if (FAST) {
         uint8_t *Yp = Y + (size_t)y0 * W + x0;
+        if (LUMA) {
 #pragma unroll
-        for (int t = 0; t < 2; t++) { const int wd = lane + 32 * t, r = wd >> 2, j = wd & 3; *(uint32_t *)(Yp + (size_t)r * W + 4 * j) = S.Yt[1 + r][1 + j]; }
-        const int c = lane >> 4, cl = lane & 15, r = cl >> 1, j = cl & 1;
-        *(uint32_t *)((c ? Cr : Cb) + (size_t)(yc0 + r) * Wc + xc0 + 4 * j) = S.Ct[c][1 + r][1 + j];
+            for (int t = 0; t < 2; t++) { const int wd = lane + 32 * t, r = wd >> 2, j = wd & 3; *(uint32_t *)(Yp + (size_t)r * W + 4 * j) = S.Yt[1 + r][1 + j]; }
+        }
+        if (CHROMA) {
+            const int c = lane >> 4, cl = lane & 15, r = cl >> 1, j = cl & 1;
+            *(uint32_t *)((c ? Cr : Cb) + (size_t)(yc0 + r) * Wc + xc0 + 4 * j) = S.Ct[c][1 + r][1 + j];
+        }
     }
 }
 
@@ -416,7 +428,9 @@ __device__ __forceinline__ bool intra_fast_ok(const PicDev &P, int a) {
 }
 
 // Wavefront driver (see wavefront.cuh): one CTA per band of WF_ROWS MB rows, one warp per row.
-template <bool GENERIC>
+// PLANES (progressive pictures only): 3 = one wavefront for luma and chroma, 1 / 2 = the luma / chroma wavefront of the split schedule
+// (own progress counters: progress[0][row] luma or both, progress[2][row] chroma).
+template <bool GENERIC, int PLANES = 3>
 __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const PicDev *pics, int npics, int bands, int *ticket) {
     __shared__ IntraWarpSmem sm[WF_ROWS];
     __shared__ int s_prog[WF_ROWS];
@@ -436,7 +450,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
     const int per = P.mbaff ? 2 : 1;
     const int rows = P.hmb / per, wmb = P.wmb;
     if (row >= rows) return;
-    RowSync rs = rs_init(s_prog, s_bar, warp, row, rows, P.progress, wmb);      // progress[0][row]
+    RowSync rs = rs_init(s_prog, s_bar, warp, row, rows, P.progress + (PLANES == 2 ? 2 * P.hmb : 0), wmb);      // progress[0][row], chroma wavefront: progress[2][row]
     // Intra masks of this row and of the row above.  An intra MB only has to wait for the row above if one of its
     // neighbours B, C, D there is itself intra: inter neighbours were completed by k_inter before this kernel
     // started.  In P/B pictures, where intra MBs are scattered, this removes the false chains a plain
@@ -489,14 +503,15 @@ __global__ void __launch_bounds__(WF_THREADS, 1024 / WF_THREADS) k_intra(const P
             const int x = xb + __ffs(mask) - 1;
             mask &= mask - 1;
             int need = min(x + 2, wmb);
-            if (masks_ok) need = above_intra(x + 1) ? x + 2 : above_intra(x) ? x + 1 : above_intra(x - 1) ? x : 0;
+            if (masks_ok) need = (PLANES != 2 && above_intra(x + 1)) ? x + 2 : above_intra(x) ? x + 1 : above_intra(x - 1) ? x : 0;      // chroma prediction has no top-right neighbour
+            else if (PLANES == 2) need = min(x + 1, wmb);
             prefetch_mb(next_intra(x));
             rs_wait(rs, need, x, lane);
             for (int s = 0; s < per; s++) {
                 const int a = (row * wmb + x) * per + s;
                 const H264B2MbInfo I = P.info[a];
                 if (I.mb_class >= H264B2_MB_I4x4 && I.mb_class <= H264B2_MB_IPCM) {
-                    if (!GENERIC || intra_fast_ok(P, a)) intra_mb<true>(P, a, I, lane, sm[warp], s_tab4, s_tab8); else intra_mb<false>(P, a, I, lane, sm[warp], s_tab4, s_tab8);
+                    if (!GENERIC || intra_fast_ok(P, a)) intra_mb<true, PLANES>(P, a, I, lane, sm[warp], s_tab4, s_tab8); else intra_mb<false, 3>(P, a, I, lane, sm[warp], s_tab4, s_tab8);
                 }
             }
             rs_publish(rs, x + 1, lane);
