@@ -477,13 +477,13 @@ def main():
     achieved = round(mc_db_bytes / (mc_db_ms / 1000.0) / 1e9, 1) if mc_db_ms > 0 else None
     dom_ms = mc_db_ms
     # DRAM traffic from the ncu --set full capture of THIS build (tools/gpu_traffic.sh + tools/make_traffic.py write
-    # profiles/traffic_r02.json with the library's SHA-1); a capture of another build is not reported
-    traffic, traffic_src = None, "no ncu capture of this build (profiles/traffic_r02.json absent or of another libh264b2.so)"
+    # profiles/traffic_r02.json with the SHA-1 of the engine sources); a capture of other sources is not reported
+    traffic, traffic_src = None, "no ncu capture of these sources (profiles/traffic_r02.json absent or of another source state)"
     try:
         import hashlib
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
-        lib_sha = hashlib.sha1(open(engine.library_path(), "rb").read()).hexdigest()
-        if tr.get("lib_sha1") == lib_sha:
+        from h264_video_decoder_demo_b200 import build as _b
+        if tr.get("src_sha1") == _b.source_hash() and "H264B2_LIB" not in os.environ:
             per_pic = sum((tr.get(k) or {}).get("dram_bytes_per_picture") or 0 for k in ("k_inter", "k_deblock", "k_bs"))
             traffic = int(per_pic * S) if per_pic else None      # per launch = per picture x pictures per launch
             traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum of this build (profiles/traffic_r02.json): MC + bS + deblock kernels, per batch of %d pictures" % S

@@ -47,6 +47,16 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the B200 engine cannot be built (there is no CPU fallback)")
 
 
+def source_hash():
+    """SHA-1 over the CUDA engine's sources (the compiled library is not bit-reproducible): what profiles/traffic_r02.json is keyed by."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted([os.path.join(CSRC, x) for x in SOURCES + HEADERS] + [os.path.join(_ROOT, "include", "h264_recon_b200.h")]):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

@@ -6,5 +6,5 @@ TAG=${1:-r02}
 mkdir -p gpurun_out
 timeout 600 ncu --set full --clock-control none -k regex:"k_inter_tma|k_inter_list|k_deblock3|k_bs_prog2" -c 36 -f -o /tmp/prof_$TAG python bench.py --streams 128 --max-pictures 10 --steps 1 --warmup 1 --no-e2e --no-cpu --no-bitstream --no-configs > gpurun_out/ncu_full_$TAG.log 2>&1
 ncu -i /tmp/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_$TAG.raw.csv 2>/dev/null
-sha1sum h264_video_decoder_demo_b200/libh264b2.so > gpurun_out/prof_$TAG.libsha1
+python -c "from h264_video_decoder_demo_b200 import build as b; print(b.source_hash())" > gpurun_out/prof_$TAG.libsha1
 ls -la gpurun_out/ | tail -5

@@ -1,6 +1,6 @@
 """Turn an `ncu --set full` report of the first pass of `bench.py --streams 128 --max-pictures 10` (tools/gpu_traffic.sh) into
 profiles/traffic_r02.json: DRAM bytes per launch / per picture of every hot kernel NEXT TO the algorithmic bytes of exactly the pictures
-those launches reconstructed, and the SHA-1 of the library that was profiled (bench.py reports `roofline.traffic` only for that build).
+those launches reconstructed, and the SHA-1 of the engine sources that were profiled (h264_video_decoder_demo_b200/build.py: source_hash; bench.py reports `roofline.traffic` only for that source state — the compiled library is not bit-reproducible).
 usage: python tools/make_traffic.py gpurun_out/prof_r02.ncu-rep gpurun_out/prof_r02.libsha1 [streams]"""
 import csv
 import json
@@ -30,7 +30,7 @@ def main(rep, shafile, streams=128):
                 "k_intra": list(range(len(rp.pictures))), "k_residual": list(range(len(rp.pictures)))}
     alg_key = {"k_inter_tma": "inter", "k_inter_list": "inter", "k_deblock3": "deblock", "k_bs_prog2": "deblock", "k_intra": "intra", "k_residual": None}
     res = {"source": "ncu --set full --clock-control none over the first pass of bench.py --streams %d --max-pictures 10 (tools/gpu_traffic.sh)" % streams,
-           "lib_sha1": open(shafile).read().split()[0], "streams_per_launch": streams, "kernels": {}}
+           "src_sha1": open(shafile).read().split()[0], "streams_per_launch": streams, "kernels": {}}
     seen = {}
     for r in data:
         name = r[ki].split("(")[0].replace("void ", "").split("<")[0]
