@@ -108,42 +108,46 @@ __global__ void __launch_bounds__(256) k_residual(const PicDev *pics) {
                 out[((y >> 2) * 4 + (x >> 2)) * 16 + (y & 3) * 4 + (x & 3)] = sat_res((d[j] + 32) >> 6);
             }
         }
-    } else if (lane < 16) {
-        // ---- luma 4x4: lane = luma4x4BlkIdx
+    }
+    // ---- 4x4 blocks: luma lanes 0..15 (lane = luma4x4BlkIdx; not with the 8x8 transform) and chroma lanes 16..23 (c = Cb/Cr, b = block) run
+    //      ONE copy of the 4x4 dequantisation + transform together (they used to be two divergent sections, executed one after the other)
+    const int16_t *lv4 = nullptr;
+    int16_t *dst4 = nullptr;
+    int dc4 = 0, dcf4 = 0, qp4 = qp;
+    bool do4 = false;
+    if (!t8 && lane < 16) {
         const int b = lane;
         const int is16 = cls == H264B2_MB_I16x16;
-        const int16_t *lv = ((m >> b) & 1) ? q + 16 * __popc(m & ((1u << b) - 1)) : nullptr;
-        int dc = 0;
+        lv4 = ((m >> b) & 1) ? q + 16 * __popc(m & ((1u << b) - 1)) : nullptr;
         if (is16 && (m & H264B2_CM_LUMA_DC)) {
             int dcY[16];
             luma_dc16_thread(pldc, qp, ls4[(qp % 6) * 16], sf, dcY);     // redundant per lane, no communication
             const int idx = (blk_y(b) >> 2) * 4 + (blk_x(b) >> 2);
 #pragma unroll
-            for (int j = 0; j < 16; j++) if (j == idx) dc = dcY[j];
+            for (int j = 0; j < 16; j++) if (j == idx) dc4 = dcY[j];
         }
-        if (lv || (is16 && (m & H264B2_CM_LUMA_DC)) || full) {
-            int16_t r[16];
-            resid4x4_thread(lv, dc, is16, qp, ls4, sf, r, 4);
-            store_blk16(out + ((blk_y(b) >> 2) * 4 + (blk_x(b) >> 2)) * 16, r);
-        }
-    }
-    // ---- chroma: lanes 16..23 (c = Cb/Cr, b = block)
-    if (lane >= 16 && lane < 24) {
+        dcf4 = is16;
+        do4 = lv4 || (is16 && (m & H264B2_CM_LUMA_DC)) || full;
+        dst4 = out + ((blk_y(b) >> 2) * 4 + (blk_x(b) >> 2)) * 16;
+    } else if (lane >= 16 && lane < 24) {
         const int c = (lane - 16) >> 2, b = (lane - 16) & 3;
         if (chroma_blk_coded(m, c, b) || full) {
-            const int qpc = chroma_qp(P, qp, c);
-            int dc = 0;
+            qp4 = chroma_qp(P, qp, c);
             if (m & H264B2_CM_CHROMA_DC) {                   // PB:3989
                 const int16_t *s = pcdc + 4 * c;
                 const int e00 = s[0] + s[2], e01 = s[1] + s[3], e10 = s[0] - s[2], e11 = s[1] - s[3];
                 const int f = b == 0 ? e00 + e01 : b == 1 ? e00 - e01 : b == 2 ? e10 + e11 : e10 - e11;
-                dc = ((f * (int)ls4[(qpc % 6) * 16]) << (qpc / 6)) >> 5;
+                dc4 = ((f * (int)ls4[(qp4 % 6) * 16]) << (qp4 / 6)) >> 5;
             }
             const uint32_t below = (c ? (m >> 22) : (m >> 18)) & ((1u << b) - 1);
-            const int16_t *lv = ((m >> ((c ? 22 : 18) + b)) & 1) ? (c ? pcr : pcb) + 16 * __popc(below) : nullptr;
-            int16_t r[16];
-            resid4x4_thread(lv, dc, 1, qpc, ls4, sf, r, 4);
-            store_blk16(out + (16 + c * 4 + b) * 16, r);
+            lv4 = ((m >> ((c ? 22 : 18) + b)) & 1) ? (c ? pcr : pcb) + 16 * __popc(below) : nullptr;
+            dcf4 = 1; do4 = true;
+            dst4 = out + (16 + c * 4 + b) * 16;
         }
+    }
+    if (do4) {
+        int16_t r[16];
+        resid4x4_thread(lv4, dc4, dcf4, qp4, ls4, sf, r, 4);
+        store_blk16(dst4, r);
     }
 }
