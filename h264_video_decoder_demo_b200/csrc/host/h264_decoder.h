@@ -88,7 +88,8 @@ struct Front {
     int wmb = 0, hmb = 0, nmb = 0;
     std::vector<MbT> mbs;
     std::vector<H264B2MbInfo> info; std::vector<uint64_t> modes; std::vector<uint32_t> coff;
-    std::vector<int16_t> coefs; std::vector<H264B2Weight> weights;
+    std::vector<int16_t> coefs; size_t ncoef = 0;      // coefs is raw storage (grown ahead of the writer, never shrunk), ncoef the levels written for this picture
+    std::vector<H264B2Weight> weights;
     int has_inter = 0, pic_active = 0;
     SliceHeader pic_sh;          // header of the last slice of the picture (what the reference keeps in the picture)
     // slice state

@@ -142,7 +142,7 @@ void Front::start_picture_storage() {
     mbs.resize(nmb); memset(mbs.data(), 0, sizeof(MbT) * nmb);
     info.resize(nmb); memset(info.data(), 0, sizeof(H264B2MbInfo) * nmb);
     modes.assign(nmb, 0); coff.assign(nmb, 0);
-    coefs.clear();
+    ncoef = 0;
     weights.clear();
     H264B2Weight d; memset(&d, 0, sizeof d); for (int c = 0; c < 3; c++) { d.w0[c] = 1; d.w1[c] = 1; }
     weights.push_back(d);
@@ -449,12 +449,13 @@ void Front::emit_picture(int deblock_enable) {
     for (int a = 0; a < nmb; a++) if (info[a].mb_class == H264B2_MB_NA) { n_na++; if (a < first_na) first_na = a; }
     bool flat = true;
     for (int l = 0; l < 6 && flat; l++) { for (int k = 0; k < 16; k++) if (h.ScalingList4x4[l][k] != 16) flat = false; for (int k = 0; k < 64; k++) if (h.ScalingList8x8[l][k] != 16) flat = false; }
-    { uint32_t next = (uint32_t)coefs.size(); for (int a = nmb - 1; a >= 0; a--) { if (info[a].mb_class == H264B2_MB_NA) coff[a] = next; else next = coff[a]; } }
-    while (coefs.size() % 4) coefs.push_back(0);
+    { uint32_t next = (uint32_t)ncoef; for (int a = nmb - 1; a >= 0; a--) { if (info[a].mb_class == H264B2_MB_NA) coff[a] = next; else next = coff[a]; } }
+    if (coefs.size() < ncoef + 4) coefs.resize(ncoef + 4);
+    while (ncoef % 4) coefs[ncoef++] = 0;
     const size_t b_info = (size_t)nmb * sizeof(H264B2MbInfo), b_modes = (size_t)nmb * 8, b_coff = (size_t)nmb * 4, b_mot = !has_inter ? 0 : packed_motion ? h264b2_pack_coefs_bound((uint32_t)nmb * (uint32_t)(sizeof(H264B2MbMotion) / 2)) : (size_t)nmb * sizeof(H264B2MbMotion);
-    const bool pack = packed_coefs && !coefs.empty();
+    const bool pack = packed_coefs && ncoef != 0;
     size_t pack_slack = 0;
-    const size_t b_w = weights.size() * sizeof(H264B2Weight), b_c = pack ? h264b2_pack_coefs_bound((uint32_t)coefs.size()) : coefs.size() * 2, b_ls = flat ? 0 : (size_t)(2 * 2 * 6 * 16 + 2 * 2 * 6 * 64) * 2;
+    const size_t b_w = weights.size() * sizeof(H264B2Weight), b_c = pack ? h264b2_pack_coefs_bound((uint32_t)ncoef) : ncoef * 2, b_ls = flat ? 0 : (size_t)(2 * 2 * 6 * 16 + 2 * 2 * 6 * 64) * 2;
     // every array starts on a 64-byte boundary inside the block: the engine keeps host alignment on the device and its kernels
     // read records with 16-byte loads
     auto al = [](size_t n) { return (n + 63) & ~(size_t)63; };
@@ -467,7 +468,7 @@ void Front::emit_picture(int deblock_enable) {
     ph.decode_idx = s.decode_idx; ph.dst_surface = cur; ph.clear_surface = n_na > 0; ph.has_inter = has_inter; ph.deblock_enable = deblock_enable;
     ph.deblock_stop_mb = first_na; ph.mbaff = h.MbaffFrameFlag; ph.cqp0 = h.pps.chroma_qp_index_offset; ph.cqp1 = h.pps.second_chroma_qp_index_offset;
     ph.n_weights = (int)weights.size(); ph.custom_scaling = !flat; ph.slice_type = h.slice_type; ph.poc = s.PicOrderCnt; ph.n_na = n_na;
-    ph.n_coefs = (uint32_t)coefs.size(); ph.nal_ref_idc = (uint32_t)h.nal_ref_idc;
+    ph.n_coefs = (uint32_t)ncoef; ph.nal_ref_idc = (uint32_t)h.nal_ref_idc;
     H264B2PicParams &p = e.params;
     p.width_mbs = wmb; p.height_mbs = hmb; p.mbaff_frame_flag = ph.mbaff; p.chroma_qp_offset[0] = ph.cqp0; p.chroma_qp_offset[1] = ph.cqp1;
     p.dst_surface = cur; p.clear_surface = ph.clear_surface; p.has_inter = has_inter; p.deblock_enable = deblock_enable; p.deblock_stop_mb = first_na;
@@ -486,7 +487,7 @@ void Front::emit_picture(int deblock_enable) {
         memcpy(q, weights.data(), b_w); p.weights = (const H264B2Weight *)q; q += al(b_w);
         if (pack) {
             size_t used = 0;
-            if (h264b2_pack_coefs(coefs.data(), (uint32_t)coefs.size(), q, b_c, &used)) error = "coefficient packing failed";
+            if (h264b2_pack_coefs(coefs.data(), (uint32_t)ncoef, q, b_c, &used)) error = "coefficient packing failed";
             p.packed |= H264B2_PACKED_COEFS;
             pack_slack += al(b_c) - al(used);
         } else if (b_c) memcpy(q, coefs.data(), b_c);

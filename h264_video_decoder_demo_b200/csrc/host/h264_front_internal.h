@@ -139,38 +139,72 @@ struct Cabac {
     // reads the stream (I_PCM samples, re-initialisation).  `offset` is only kept for init / diagnostics.
     uint64_t V = 0; int k = 0;
     inline void sync() { br->pos -= k; V >>= k; k = 0; }
-    inline void refill() { V = (V << 32) | br->peek(32); br->pos += 32; k += 32; }
+    __attribute__((noinline)) void refill() { V = (V << 32) | br->peek(32); br->pos += 32; k += 32; }
     void init_engine(BitReader *b) { if (br && k) sync(); br = b; range = 510; offset = br->u(9); V = offset; k = 0; }      // re-initialisation inside a slice (I_PCM)
     void start_slice(BitReader *b) { br = b; range = 510; offset = br->u(9); V = offset; k = 0; }                          // the look-ahead of the previous slice is void
-    inline int decision(int ctx) {
+    __attribute__((always_inline)) inline int decision(int ctx) {
+        // branch-free except for the refill (once per 32 bits): which symbol was decoded and whether a renormalisation follows are
+        // both close to coin flips for the coefficient contexts, a mispredicted branch costs more than the whole arithmetic
         const uint32_t s = state[ctx];
         const uint32_t rlps = g_range_lps[s >> 1][(range >> 6) & 3];
-        range -= rlps;
-        const uint64_t scaled = (uint64_t)range << k;
-        if (V < scaled) {
-            state[ctx] = g_next_state[0][s];
-            if (range < 256) { range <<= 1; if (k == 0) refill(); k--; }      // the MPS path needs at most one shift
-            return (int)(s & 1);
-        }
-        V -= scaled; range = rlps;
-        state[ctx] = g_next_state[1][s];
-        const int n = __builtin_clz(range) - 23; range <<= n;
+        const uint32_t rmps = range - rlps;
+        const uint64_t scaled = (uint64_t)rmps << k;
+        const uint32_t lps = V >= scaled;                 // 1: least probable symbol
+        V -= lps ? scaled : 0;
+        uint32_t r = lps ? rlps : rmps;
+        state[ctx] = g_next_state[0][(lps << 7) | s];      // [1][s] follows [0][127]
+        const int n = __builtin_clz(r) - 23;               // r in [6, 510] -> 0..6 (0 or 1 after an MPS)
+        range = r << n;
         if (k < n) refill();
         k -= n;
-        return (int)((s & 1) ^ 1);
+        return (int)((s & 1) ^ lps);
     }
     inline int bypass() {
         if (k == 0) refill();
         k--;
         const uint64_t scaled = (uint64_t)range << k;
-        if (V >= scaled) { V -= scaled; return 1; }
-        return 0;
+        const uint32_t b = V >= scaled;          // signs and suffix bits are coin flips: no branch
+        V -= b ? scaled : 0;
+        return (int)b;
     }
     inline int terminate() {
         range -= 2;
         if (V >= ((uint64_t)range << k)) return 1;
         if (range < 256) { const int n = __builtin_clz(range) - 23; range <<= n; if (k < n) refill(); k -= n; }
         return 0;
+    }
+};
+
+// The decoder's registers as locals of one syntax function (the residual loops): `state` is a byte array, so a store into it may alias
+// range / V / k of the Cabac object and the compiler keeps them in memory; a CabacRegs whose address never escapes lives in
+// registers.  Same arithmetic as Cabac::decision / bypass; written back by the destructor.
+struct CabacRegs {
+    Cabac &c; uint32_t range; uint64_t V; int k; uint8_t *const st; const uint8_t (*const lps)[4]; const uint8_t *const next;
+    explicit CabacRegs(Cabac &cc) : c(cc), range(cc.range), V(cc.V), k(cc.k), st(cc.state), lps(g_range_lps), next(&g_next_state[0][0]) {}
+    ~CabacRegs() { c.range = range; c.V = V; c.k = k; }
+    __attribute__((noinline)) void refill() { V = (V << 32) | c.br->peek(32); c.br->pos += 32; k += 32; }
+    __attribute__((always_inline)) inline int decision(int ctx) {
+        const uint32_t s = st[ctx];
+        const uint32_t rlps = lps[s >> 1][(range >> 6) & 3];
+        const uint32_t rmps = range - rlps;
+        const uint64_t scaled = (uint64_t)rmps << k;
+        const uint32_t l = V >= scaled;
+        V -= l ? scaled : 0;
+        const uint32_t r = l ? rlps : rmps;
+        st[ctx] = next[(l << 7) | s];
+        const int n = __builtin_clz(r) - 23;
+        range = r << n;
+        if (__builtin_expect(k < n, 0)) refill();
+        k -= n;
+        return (int)((s & 1) ^ l);
+    }
+    __attribute__((always_inline)) inline int bypass() {
+        if (__builtin_expect(k == 0, 0)) refill();
+        k--;
+        const uint64_t scaled = (uint64_t)range << k;
+        const uint32_t b = V >= scaled;
+        V -= b ? scaled : 0;
+        return (int)b;
     }
 };
 

@@ -9,7 +9,18 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <emmintrin.h>      // SSE2 is part of the x86-64 baseline
 
+#ifdef FE_PROF
+#include <x86intrin.h>
+unsigned long long g_prof[16];
+struct ProfDump { ~ProfDump() { const char *n[] = {"mb_layer(all)", "residual", "inter_pred", "intra_modes", "emit_mb", "skip_mb", "slice_total", "cbf_ctx", "cbf+sigmap", "mb_type", "pred_syntax", "cbp+qpd", "skipflag+term"}; for (int i = 0; i < 13; i++) fprintf(stderr, "%-14s %8.1f Mcycles\n", n[i], g_prof[i] / 1e6); } } g_profdump;
+#define PROF_T(v) const unsigned long long v = __rdtsc()
+#define PROF_ADD(i, v) g_prof[i] += __rdtsc() - v
+#else
+#define PROF_T(v)
+#define PROF_ADD(i, v)
+#endif
 namespace h264b2 {
 
 namespace {
@@ -354,7 +365,9 @@ struct Dec {
         static const int cbfOff[5] = {0, 4, 8, 12, 16}, sigOff[5] = {0, 15, 29, 44, 47}, absOff[5] = {0, 10, 20, 30, 39};
         MbT &m = mbs[cur];
         int coded = 1;
+        PROF_T(tc);
         if (maxNumCoeff != 64) coded = cb.decision(85 + cbfOff[cat] + cbf_ctx(cat, blk, comp));
+        PROF_ADD(7, tc);
         memset(lvl, 0, sizeof(int32_t) * maxNumCoeff);
         if (!coded) return 0;
         const int fld = m.field;
@@ -368,32 +381,36 @@ struct Dec {
         const uint8_t *lastInc = cat == CAT_LUMA8 ? kLast8 : cat == CAT_CDC ? cdcInc : ident;
         uint8_t where[64];            // positions of the significant coefficients, in scan order
         int nsig = 0, numCoeff = endIdx + 1, i = startIdx;
+        {
+        CabacRegs r(cb);
         while (i < numCoeff - 1) {
-            if (cb.decision(sigBase + sigInc[i])) {
+            if (r.decision(sigBase + sigInc[i])) {
                 where[nsig++] = (uint8_t)i;
-                if (cb.decision(lastBase + lastInc[i])) { numCoeff = i + 1; break; }
+                if (r.decision(lastBase + lastInc[i])) { numCoeff = i + 1; break; }
             }
             i++;
         }
         if (nsig == 0 || where[nsig - 1] != numCoeff - 1) where[nsig++] = (uint8_t)(numCoeff - 1);     // the last position is significant by inference
+        PROF_ADD(8, tc);
         int eq1 = 0, gt1 = 0;
         const int gtMax = 4 - (cat == CAT_CDC ? 1 : 0);
         for (int k = nsig - 1; k >= 0; k--) {
             int ctx = absBase + (gt1 != 0 ? 0 : std::min(4, 1 + eq1));
             int v = 0;
-            if (cb.decision(ctx)) {
+            if (r.decision(ctx)) {
                 ctx = absBase + 5 + std::min(gtMax, gt1);
                 v = 1;
-                while (v < 14 && cb.decision(ctx)) v++;
+                while (v < 14 && r.decision(ctx)) v++;
                 if (v >= 14) {
                     int e = 0; bool cut = false;
-                    while (cb.bypass()) { v += 1 << e; e++; if (e >= 18) { cut = true; break; } }      // REF: H264Cabac.cpp:4905 stops without the suffix bits
-                    if (!cut) while (e--) v += cb.bypass() << e;
+                    while (r.bypass()) { v += 1 << e; e++; if (e >= 18) { cut = true; break; } }      // REF: H264Cabac.cpp:4905 stops without the suffix bits
+                    if (!cut) while (e--) v += r.bypass() << e;
                 }
             }
             const int a = v + 1;
             if (a == 1) eq1++; else gt1++;
-            lvl[where[k]] = cb.bypass() ? -a : a;
+            lvl[where[k]] = r.bypass() ? -a : a;
+        }
         }
         const int total = nsig;
         if (cat == CAT_I16DC || cat == CAT_CDC) m.cbf_dc ^= (uint8_t)(1 << (comp + 1));
@@ -677,7 +694,9 @@ struct Dec {
         MbT &m = mbs[cur];
         set_common(m);
         const int st = sh.slice_type;
+        PROF_T(t1);
         int mb_type = cabac ? cabac_mb_type() : (int)br.ue();
+        PROF_ADD(9, t1);
         if (mb_type < 0) return -1;
         int it = -1;      // I mb_type
         if (st == SLICE_I) { if (mb_type > 25) return -1; it = mb_type; }
@@ -693,6 +712,7 @@ struct Dec {
             for (int i = 0; i < 384; i++) pcm[i] = (int16_t)br.u(8);
         } else {
             int noSub8x8 = 1;
+            PROF_T(t2);
             if (m.type == T_P8x8 || m.type == T_P8x8ref0 || m.type == T_B8x8) { if (sub_mb_pred(m, &noSub8x8)) return -1; }
             else {
                 if (sh.pps.transform_8x8_mode_flag && m.type == T_I_NxN) {
@@ -708,6 +728,8 @@ struct Dec {
                     m.chroma_pred = (uint8_t)(cabac ? cabac_intra_chroma_pred_mode() : br.ue());
                 } else if (m.type != T_BDIRECT) { if (mb_pred_inter(m)) return -1; }
             }
+            PROF_ADD(10, t2);
+            PROF_T(t3);
             if (m.type != T_I16) {
                 int cbp;
                 if (cabac) cbp = cabac_cbp();
@@ -718,9 +740,13 @@ struct Dec {
             }
             if (m.cbp_luma > 0 || m.cbp_chroma > 0 || m.type == T_I16) {
                 int d = cabac ? cabac_mb_qp_delta() : br.se();
+                PROF_ADD(11, t3);
                 if (d == QP_DELTA_ERROR) return -1;
                 m.qp_delta = (int8_t)std::max(-128, std::min(127, d));
-                if (residual()) return -1;
+                PROF_T(tr);
+                const int rr = residual();
+                PROF_ADD(1, tr);
+                if (rr) return -1;
                 residual_ok = true;
                 if (d < -26 || d > 25) d = d < -26 ? -26 : 25;
                 m.qp_delta = (int8_t)d;
@@ -947,9 +973,14 @@ struct Dec {
             if (!is8x8 && !direct16) nsub = 1;
             else if (is8x8 && !subDirect) { static const int ns[4] = {1, 2, 2, 4}; nsub = ns[m.sub_shape[p]]; }
             else nsub = 4;
+            // direct_8x8_inference: the four 4x4 blocks of a direct quadrant share the co-located corner block (5 * p), the reference
+            // indices and both predictors, so they get identical results — derived once for the whole 8x8
+            const bool direct8 = (direct16 || subDirect) && sh.sps.direct_8x8_inference_flag;
+            if (direct8) nsub = 1;
             for (int s = 0; s < nsub; s++) {
                 int x, y, w, h;
-                if (direct16 || subDirect) { x = (p % 2) * 8 + (s % 2) * 4; y = (p / 2) * 8 + (s / 2) * 4; w = h = 4; }
+                if (direct8) { x = (p % 2) * 8; y = (p / 2) * 8; w = h = 8; }
+                else if (direct16 || subDirect) { x = (p % 2) * 8 + (s % 2) * 4; y = (p / 2) * 8 + (s / 2) * 4; w = h = 4; }
                 else part_rect(m, p, s, &x, &y, &w, &h);
                 int pf[2] = {0, 0};
                 if (m.type == T_PSKIP) {
@@ -1028,18 +1059,38 @@ struct Dec {
     }
 
     // ------------------------------------------------------------ SoA emission of one macroblock
-    static bool anynz(const int32_t *s, int n) { for (int i = 0; i < n; i++) if (s[i]) return true; return false; }
-    void put16(const int32_t *src, int n, int shift_in) {
-        const size_t o = F.coefs.size();
-        F.coefs.resize(o + n);
-        int16_t *dst = F.coefs.data() + o;
-        if (shift_in) { dst[0] = 0; for (int k = 1; k < n; k++) { int32_t v = src[k - 1]; dst[k] = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); } }
-        else for (int k = 0; k < n; k++) { int32_t v = src[k]; dst[k] = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
+    // Levels travel as int16 (saturated, like the container the reference harness writes) and only blocks with a non-zero level are
+    // present.  One pass: saturating pack, OR of everything, store at the write position; the position advances only when something was
+    // non-zero.  n = 8 (both chroma DC blocks), 16 or 64; shift_in: AC blocks of 15 levels are stored as [0, level 0..14].
+    int16_t *cdst = nullptr;
+    inline bool put_if_nz(const int32_t *src, int n, int shift_in) {
+        const __m128i zero = _mm_setzero_si128();
+        __m128i any;
+        if (shift_in) {
+            const __m128i a0 = _mm_loadu_si128((const __m128i *)src), a1 = _mm_loadu_si128((const __m128i *)(src + 4)), a2 = _mm_loadu_si128((const __m128i *)(src + 8));
+            const __m128i a3 = _mm_and_si128(_mm_loadu_si128((const __m128i *)(src + 12)), _mm_set_epi32(0, -1, -1, -1));      // src[15] is not part of the block
+            const __m128i p0 = _mm_packs_epi32(a0, a1), p1 = _mm_packs_epi32(a2, a3);
+            any = _mm_or_si128(p0, p1);
+            _mm_storeu_si128((__m128i *)cdst, _mm_slli_si128(p0, 2));
+            _mm_storeu_si128((__m128i *)(cdst + 8), _mm_or_si128(_mm_slli_si128(p1, 2), _mm_srli_si128(p0, 14)));
+        } else {
+            any = zero;
+            for (int k = 0; k < n; k += 8) {
+                const __m128i pk = _mm_packs_epi32(_mm_loadu_si128((const __m128i *)(src + k)), _mm_loadu_si128((const __m128i *)(src + k + 4)));
+                any = _mm_or_si128(any, pk);
+                _mm_storeu_si128((__m128i *)(cdst + k), pk);
+            }
+        }
+        if (_mm_movemask_epi8(_mm_cmpeq_epi8(any, zero)) == 0xffff) return false;
+        cdst += n;
+        return true;
     }
     void emit_mb(bool have_residual) {
         const MbT &m = mbs[cur];
         H264B2MbInfo &I = F.info[cur];
-        F.coff[cur] = (uint32_t)F.coefs.size();
+        if (F.coefs.size() < F.ncoef + 1024) F.coefs.resize(std::max(F.coefs.size() * 2, F.ncoef + ((size_t)1 << 18)));      // a macroblock writes <= 408 levels
+        cdst = F.coefs.data() + F.ncoef;
+        F.coff[cur] = (uint32_t)F.ncoef;
         I.mb_class = m.cls;
         const bool spsi = sh.slice_type == SLICE_SP || sh.slice_type == SLICE_SI;
         I.flags = (uint8_t)((m.field ? H264B2_MBF_FIELD : 0) | (m.t8x8 ? H264B2_MBF_T8x8 : 0) | (spsi ? H264B2_MBF_SPSI : 0) | ((m.pm0_inter && sh.pps.constrained_intra_pred_flag) ? H264B2_MBF_CIP_UNAVAIL : 0));
@@ -1047,23 +1098,25 @@ struct Dec {
         I.qpy = m.qp;
         I.slice_number = m.slice;
         uint16_t nnz = 0;
-        for (int b = 0; b < 16; b++) if (m.t8x8 ? m.nnz8[b >> 2] > 0 : m.nnz[b] > 0) nnz |= (uint16_t)(1u << b);
+        if (m.t8x8) { for (int q = 0; q < 4; q++) if (m.nnz8[q]) nnz |= (uint16_t)(0xFu << (4 * q)); }
+        else nnz = (uint16_t)~_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i *)m.nnz), _mm_setzero_si128()));
         I.nnz_mask = nnz;
         I.filter_offset_a = (int8_t)sh.FilterOffsetA; I.filter_offset_b = (int8_t)sh.FilterOffsetB; I.deblock_idc = (uint8_t)sh.disable_deblocking_filter_idc;
         uint32_t cm = 0;
-        if (m.cls == H264B2_MB_IPCM) { cm |= H264B2_CM_PCM; for (int i = 0; i < 384; i++) F.coefs.push_back(pcm[i]); }
+        if (m.cls == H264B2_MB_IPCM) { cm |= H264B2_CM_PCM; memcpy(cdst, pcm, sizeof pcm); cdst += 384; }
         else if (have_residual && coded) {
             // a block is present iff it has a non-zero level (oracle/ref_harness.cpp); only parsed blocks (TotalCoeff > 0) can have one
             const uint32_t cd = coded;
             if (m.cls == H264B2_MB_I16x16) {
-                for (int b = 0; b < 16; b++) if ((cd >> b) & 1) if (anynz(i16ac[b], 15)) { cm |= H264B2_CM_LUMA(b); put16(i16ac[b], 16, 1); }
-                if ((cd >> 16) & 1) if (anynz(i16dc, 16)) { cm |= H264B2_CM_LUMA_DC; put16(i16dc, 16, 0); }
-            } else if (m.t8x8) { for (int b = 0; b < 4; b++) if ((cd >> b) & 1) if (anynz(l8[b], 64)) { cm |= H264B2_CM_LUMA(b); put16(l8[b], 64, 0); } }
-            else for (int b = 0; b < 16; b++) if ((cd >> b) & 1) if (anynz(l4[b], 16)) { cm |= H264B2_CM_LUMA(b); put16(l4[b], 16, 0); }
-            if ((cd >> 17) & 1) if (anynz(cdc[0], 4) || anynz(cdc[1], 4)) { cm |= H264B2_CM_CHROMA_DC; put16(cdc[0], 4, 0); put16(cdc[1], 4, 0); }
-            for (int b = 0; b < 4; b++) if ((cd >> (18 + b)) & 1) if (anynz(cac[0][b], 15)) { cm |= H264B2_CM_CB(b); put16(cac[0][b], 16, 1); }
-            for (int b = 0; b < 4; b++) if ((cd >> (22 + b)) & 1) if (anynz(cac[1][b], 15)) { cm |= H264B2_CM_CR(b); put16(cac[1][b], 16, 1); }
+                for (int b = 0; b < 16; b++) if ((cd >> b) & 1) if (put_if_nz(i16ac[b], 16, 1)) cm |= H264B2_CM_LUMA(b);
+                if ((cd >> 16) & 1) if (put_if_nz(i16dc, 16, 0)) cm |= H264B2_CM_LUMA_DC;
+            } else if (m.t8x8) { for (int b = 0; b < 4; b++) if ((cd >> b) & 1) if (put_if_nz(l8[b], 64, 0)) cm |= H264B2_CM_LUMA(b); }
+            else for (int b = 0; b < 16; b++) if ((cd >> b) & 1) if (put_if_nz(l4[b], 16, 0)) cm |= H264B2_CM_LUMA(b);
+            if ((cd >> 17) & 1) if (put_if_nz(cdc[0], 8, 0)) cm |= H264B2_CM_CHROMA_DC;      // cdc[0] and cdc[1] are contiguous: Cb DC then Cr DC
+            for (int b = 0; b < 4; b++) if ((cd >> (18 + b)) & 1) if (put_if_nz(cac[0][b], 16, 1)) cm |= H264B2_CM_CB(b);
+            for (int b = 0; b < 4; b++) if ((cd >> (22 + b)) & 1) if (put_if_nz(cac[1][b], 16, 1)) cm |= H264B2_CM_CR(b);
         }
+        F.ncoef = (size_t)(cdst - F.coefs.data());
         I.coef_mask = cm;
         if (m.cls == H264B2_MB_I4x4) { uint64_t v = 0; for (int b = 0; b < 16; b++) v |= (uint64_t)(m.ipred[b] & 15) << (4 * b); F.modes[cur] = v; }
         if (m.cls == H264B2_MB_I8x8) { uint64_t v = 0; for (int b = 0; b < 4; b++) v |= (uint64_t)(m.ipred[b] & 15) << (4 * b); F.modes[cur] = v; }
@@ -1129,7 +1182,7 @@ struct Dec {
                         mbs[cur].field = (uint8_t)F.mb_field;
                     }
                     if (mbaff && cur % 2 == 1 && prevMbSkipped) F.mb_skip_flag = skipNext;
-                    else F.mb_skip_flag = cabac_mb_skip_flag(cur);
+                    else { PROF_T(t4); F.mb_skip_flag = cabac_mb_skip_flag(cur); PROF_ADD(12, t4); }
                     if (F.mb_skip_flag) {
                         if (mbaff && cur % 2 == 0) {
                             mbs[cur].skip_flag = 1;
@@ -1138,7 +1191,10 @@ struct Dec {
                             if (!skipNext) { F.mb_field = cabac_mb_field_flag(); skipReadField = true; }
                             else F.mb_field = infer_field_flag();
                         }
-                        if (skip_mb()) return -1;
+                        PROF_T(ts);
+                        const int sr = skip_mb();
+                        PROF_ADD(5, ts);
+                        if (sr) return -1;
                     }
                     moreData = !F.mb_skip_flag;
                 }
@@ -1151,17 +1207,19 @@ struct Dec {
                 S.mb_cnt++;
                 residual_ok = false;
                 mbs[cur].slice = (uint16_t)F.slice_number; mbs[cur].field = (uint8_t)F.mb_field;
-                const int r = macroblock_layer();       // a failure is logged by the reference and reconstruction goes on with what was parsed (SD:380-384)
+                PROF_T(tm);
+                const int r = macroblock_layer();
+                PROF_ADD(0, tm);       // a failure is logged by the reference and reconstruction goes on with what was parsed (SD:380-384)
                 if (r != 0) { MbT &m = mbs[cur]; if (m.type == T_NA) { /* nothing usable was parsed: the reference's reconstruction calls fail on MB_TYPE_NA */ return -1; } }
                 MbT &m = mbs[cur];
-                if (m.cls == H264B2_MB_INTER) { const int e = inter_prediction(); emit_mb(residual_ok); if (e) return -1; }
-                else { if (m.type == T_I_NxN) derive_intra_modes(); emit_mb(residual_ok); }
+                if (m.cls == H264B2_MB_INTER) { PROF_T(ti); const int e = inter_prediction(); PROF_ADD(2, ti); PROF_T(te); emit_mb(residual_ok); PROF_ADD(4, te); if (e) return -1; }
+                else { PROF_T(ti); if (m.type == T_I_NxN) derive_intra_modes(); PROF_ADD(3, ti); PROF_T(te); emit_mb(residual_ok); PROF_ADD(4, te); }
             }
             if (!cabac) moreData = br.more_rbsp_data();
             else {
                 if (st != SLICE_I && st != SLICE_SI) prevMbSkipped = F.mb_skip_flag;
                 if (mbaff && cur % 2 == 0) moreData = 1;
-                else moreData = !cb.terminate();
+                else { PROF_T(t4); moreData = !cb.terminate(); PROF_ADD(12, t4); }
             }
             cur = next_mb(cur);
             if (cur < 0) break;
@@ -1175,7 +1233,10 @@ struct Dec {
 
 int Front::decode_slice() {
     Dec d(*this);
-    return d.run();
+    PROF_T(t0);
+    const int r = d.run();
+    PROF_ADD(6, t0);
+    return r;
 }
 
 }  // namespace h264b2
