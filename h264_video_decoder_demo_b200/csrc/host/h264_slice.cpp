@@ -595,7 +595,8 @@ struct Dec {
     }
     // geometry of partition p / sub-partition s of the current macroblock
     void part_rect(const MbT &m, int p, int s, int *x, int *y, int *w, int *h) const {
-        const int px = (p % (16 / m.part_w)) * m.part_w, py = (p / (16 / m.part_w)) * m.part_h;
+        const int two = m.part_w != 16;                 // partitions per row - 1 (part_w is 8 or 16): no division
+        const int px = (p & two) * m.part_w, py = (p >> two) * m.part_h;
         if (m.type == T_P8x8 || m.type == T_P8x8ref0 || m.type == T_B8x8) {
             static const uint8_t sw[4] = {8, 8, 4, 4}, shh[4] = {8, 4, 8, 4};
             const int w_ = sw[m.sub_shape[p]], h_ = shh[m.sub_shape[p]];
