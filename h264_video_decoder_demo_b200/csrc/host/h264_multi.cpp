@@ -24,11 +24,11 @@ struct Stream {                 // one decoding unit: a whole stream, or one clo
     H264B2Front *fe = nullptr;
     std::deque<H264B2FrontEvent> q;
     int pics_queued = 0;
-    bool parsed_all = false, finished = false;
+    bool parsed_all = false, finished = false, claimed = false;      // claimed: a parser thread is inside this stream's front end
     uint64_t hash = 0;
     int ring = 0;
 };
-enum { QUEUE_DEPTH = 3, RING = 4 };
+enum { RING = 4 };
 }
 
 extern "C" int h264b2_multi_decode(int device, int n_inputs, const char *const *paths, int n_threads, int flags,
@@ -64,6 +64,9 @@ extern "C" int h264b2_multi_decode(int device, int n_inputs, const char *const *
         }
     }
     const int n_streams = (int)st.size();
+    // pictures a stream's parser may run ahead of the submit thread (H264B2_MULTI_QUEUE_DEPTH, default 3; a queued picture holds one page-locked block)
+    int QUEUE_DEPTH = 3;
+    if (const char *e = getenv("H264B2_MULTI_QUEUE_DEPTH")) { const int v = atoi(e); if (v >= 1 && v <= 64) QUEUE_DEPTH = v; }
     if (n_threads > n_streams) n_threads = n_streams;
     // picture size from the first stream (all streams of one context share it)
     int wmb = 0, hmb = 0;
@@ -98,27 +101,44 @@ extern "C" int h264b2_multi_decode(int device, int n_inputs, const char *const *
         std::vector<double> busy(n_threads, 0.0);
         const auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> pool;
+        // Parser threads claim streams dynamically: whichever unclaimed stream has the emptiest queue (so the submit thread's batches stay
+        // wide and no thread idles while another still has several streams to go — the first version dealt streams s -> thread s mod T,
+        // which left threads idle whenever T did not divide the number of streams or the streams differed in length).  One claim = one
+        // front-end event; a front end is only ever inside one thread at a time and changes hands under `mu`.
         for (int t = 0; t < n_threads; t++)
             pool.emplace_back([&, t] {
+                int next = t % n_streams;
                 for (;;) {
-                    bool all_done = true, progressed = false;
-                    for (int s = t; s < n_streams; s += n_threads) {
-                        Stream &x = st[s];
-                        { std::lock_guard<std::mutex> l(mu); if (cancel) return; if (x.parsed_all) continue; all_done = false; if (x.pics_queued >= QUEUE_DEPTH) continue; }
-                        const auto b0 = std::chrono::steady_clock::now();
-                        H264B2FrontEvent ev;
-                        const int r = h264b2_front_next(x.fe, &ev);
-                        busy[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
-                        std::lock_guard<std::mutex> l(mu);
-                        if (r < 0) { if (first_error.empty()) first_error = std::string(paths[x.owner]) + ": " + h264b2_front_last_error(x.fe); memset(&ev, 0, sizeof ev); ev.kind = H264B2_EV_END; }
-                        x.q.push_back(ev);
-                        if (ev.kind == H264B2_EV_PICTURE) x.pics_queued++;
-                        if (ev.kind == H264B2_EV_END) x.parsed_all = true;
-                        progressed = true;
-                        cv_data.notify_one();
+                    int s = -1;
+                    {
+                        std::unique_lock<std::mutex> l(mu);
+                        for (;;) {
+                            if (cancel) return;
+                            bool all_done = true; int best_q = QUEUE_DEPTH;
+                            for (int i = 0, c = next; i < n_streams; i++, c = c + 1 == n_streams ? 0 : c + 1) {
+                                const Stream &x = st[c];
+                                if (x.parsed_all) continue;
+                                all_done = false;
+                                if (!x.claimed && x.pics_queued < best_q) { s = c; best_q = x.pics_queued; }
+                            }
+                            if (all_done) return;
+                            if (s >= 0) { st[s].claimed = true; break; }
+                            cv_space.wait_for(l, std::chrono::milliseconds(2));
+                        }
                     }
-                    if (all_done) return;
-                    if (!progressed) { std::unique_lock<std::mutex> l(mu); cv_space.wait_for(l, std::chrono::milliseconds(2)); }
+                    Stream &x = st[s];
+                    const auto b0 = std::chrono::steady_clock::now();
+                    H264B2FrontEvent ev;
+                    const int r = h264b2_front_next(x.fe, &ev);
+                    busy[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+                    std::lock_guard<std::mutex> l(mu);
+                    if (r < 0) { if (first_error.empty()) first_error = std::string(paths[x.owner]) + ": " + h264b2_front_last_error(x.fe); memset(&ev, 0, sizeof ev); ev.kind = H264B2_EV_END; }
+                    x.q.push_back(ev);
+                    if (ev.kind == H264B2_EV_PICTURE) x.pics_queued++;
+                    if (ev.kind == H264B2_EV_END) x.parsed_all = true;
+                    x.claimed = false;
+                    cv_data.notify_one();
+                    next = s + 1 == n_streams ? 0 : s + 1;
                 }
             });
         // ---- submit thread (this one)
