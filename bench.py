@@ -376,7 +376,7 @@ def main():
     if not args.dense_coefs and not args.no_e2e and args.host_layout == "batch":
         need = sum(variants[var_of[s]]["extents"][pic_of(s, i)][1] for s in sids for i in range(npic)) + 4096
         avail = int(re.search(r"MemAvailable:\s+(\d+)", open("/proc/meminfo").read()).group(1)) * 1024
-        if avail > 3 * need:
+        if avail > 3 * need * world:          # every rank of the node allocates the same arena at the same moment
             host_layout = "batch"
             arena = eng.pinned_array(need)
             o = (-arena.ctypes.data) % 64
