@@ -84,7 +84,7 @@ class Stream:
     """Random syntax for `n_pics` pictures of wmb x hmb macroblocks."""
 
     def __init__(self, seed, wmb=8, hmb=6, n_pics=5, t8x8=False, weighted=False, n_refs=3, max_slices=3, pcm=True, poc_type=2, bframes=False, bipred_idc=0,
-                 mmco=False, mmco5=False, mmco_set=(1, 2, 3, 4, 6), mmco_mod=True, mmco_idr_lt=True):
+                 mmco=False, mmco5=False, mmco_set=(1, 2, 3, 4, 6), mmco_mod=True, mmco_idr_lt=True, fn_gaps=False):
         self.rng = np.random.default_rng(seed)
         self.wmb, self.hmb, self.n_pics = wmb, hmb, n_pics
         self.t8x8, self.weighted, self.n_refs, self.max_slices, self.pcm, self.poc_type = t8x8, weighted, n_refs, max_slices, pcm, poc_type
@@ -95,6 +95,9 @@ class Stream:
         # (IDR long_term_reference_flag, MMCO 3 / 6) and reference list modification with short- and long-term picture numbers
         # (H264SliceHeader.cpp:672, H264RefPicList.cpp:1299-1484, 1736-2136); P-only streams, every picture a reference
         self.mmco, self.mmco5, self.mmco_set, self.mmco_mod, self.mmco_idr_lt = mmco, mmco5, tuple(mmco_set), mmco_mod, mmco_idr_lt
+        # fn_gaps: frame_num jumps by more than one between pictures (gaps_in_frame_num_value_allowed_flag = 1); the reference's
+        # Decoding_process_for_gaps_in_frame_num is an empty stub (H264RefPicList.cpp:1598): no "non-existing" frames are inserted
+        self.fn_gaps = fn_gaps
         self.ops_log = []          # marking / list-modification operations written (coverage of the generated stream)
         self.st, self.lt, self.max_lt, self.prev_ref_fn = [], {}, -1, 0      # short-term frame_nums (decode order), long-term indices in use
         self.out = bytearray()
@@ -109,7 +112,7 @@ class Stream:
         b.ue(self.poc_type)
         if self.poc_type == 0:
             b.ue(4)
-        b.ue(self.n_refs); b.u(1, 0)
+        b.ue(self.n_refs); b.u(1, 1 if self.fn_gaps else 0)        # max_num_ref_frames, gaps_in_frame_num_value_allowed_flag
         b.ue(self.wmb - 1); b.ue(self.hmb - 1)
         b.u(1, 1); b.u(1, 1); b.u(1, 0)                              # frame_mbs_only, direct_8x8_inference, no cropping
         b.u(1, 1)                                                    # VUI: only the bitstream restriction (max_num_reorder_frames = 0)
@@ -594,8 +597,10 @@ class Stream:
                 fn = 1 if self._last_was_mmco5 else (fn + 1) & 255      # after MMCO 5 the picture counts as frame_num 0 (7.4.3)
             return bytes(self.out)
         if not self.bframes:
+            fn = 0
             for p in range(self.n_pics):
-                self.picture(p, p & 255)
+                self.picture(p, fn & 255)
+                fn += 1 + (int(self.rng.integers(1, 4)) if self.fn_gaps and self.rng.random() < 0.5 else 0)
             return bytes(self.out)
         # decode order I0 P4 B2 P8 B6 ... (POC = 2 x display index); every second B picture is itself a reference (B pyramid)
         n_ref_done, ref_pocs, k, display = 0, [], 0, 0

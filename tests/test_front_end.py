@@ -184,6 +184,39 @@ def test_marking_and_long_term_streams_against_the_live_reference(tmp_path):
     assert decoded >= 9
 
 
+def test_frame_num_gaps_are_ignored_like_the_reference(tmp_path):
+    """the reference's Decoding_process_for_gaps_in_frame_num is an empty stub that nothing calls
+    (H264RefPicList.cpp:1598) — a jump in frame_num inserts no "non-existing" frames, the sliding window and the picture numbers just
+    see the frame_nums that arrive.  Streams with gaps_in_frame_num_value_allowed_flag = 1 and random jumps: the front end's container
+    equals the live reference's field for field and the oracle reproduces the reference's pixels."""
+    import subprocess
+    import h264_writer
+    import oracle_py as O
+    from h264_video_decoder_demo_b200 import frontend, replay
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        pytest.skip("reference harness not built")
+    cfgs = [dict(n_pics=7, n_refs=3), dict(n_pics=7, n_refs=2, poc_type=0, weighted=True), dict(n_pics=6, n_refs=4, t8x8=True, max_slices=2)]
+    decoded = 0
+    for k, cfg in enumerate(cfgs * 2):
+        seed = 900 + k
+        src, ref_bin, mine_bin = str(tmp_path / "s.h264"), str(tmp_path / "ref.bin"), str(tmp_path / "mine.bin")
+        w = h264_writer.Stream(seed=seed, fn_gaps=True, **cfg)
+        open(src, "wb").write(w.build())
+        r = subprocess.run([harness, src, "--replay", ref_bin, "--quiet"], capture_output=True, text=True)
+        if r.returncode != 0 or [l for l in r.stdout.split("\n") if ("failed" in l or "Error" in l) and "open: Error" not in l]:
+            continue
+        decoded += 1
+        assert frontend.parse_to_container(src, mine_bin) == 0
+        ref, mine = replay.load_replay(ref_bin), replay.load_replay(mine_bin)
+        assert compare(mine, ref) == [], f"seed {seed} cfg {cfg}"
+        dpb = O.OracleDPB(mine.width_mbs, mine.height_mbs)
+        for a, b in zip(mine.pictures, ref.pictures):
+            dpb.reconstruct(replay.pic_params(mine, a))
+            assert dpb.checksum(a.dst_surface) == b.sum_post, f"seed {seed} cfg {cfg} picture {a.decode_idx}"
+    assert decoded >= 4
+
+
 def test_reference_mishandles_max_long_term_frame_idx(tmp_path):
     """Recorded, reproducible: streams that use memory_management_control_operation 4 (max_long_term_frame_idx_plus1) make the unmodified
     reference lose its reference lists (Reference_picture_selection_process fails, open() gives up) or crash (SIGSEGV) — most of them.
