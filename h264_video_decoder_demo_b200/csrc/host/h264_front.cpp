@@ -636,7 +636,7 @@ extern "C" int h264b2_front_write_container_range(const char *h264_path, const c
             if (max_pictures <= 0 || ev.decode_idx < max_pictures) { OutRec o; o.decode_idx = ev.decode_idx; o.pad = 0; o.sum = 0; outs.push_back(o); }
         }
     }
-    fwrite(outs.data(), sizeof(OutRec), outs.size(), fo);
+    if (!outs.empty()) fwrite(outs.data(), sizeof(OutRec), outs.size(), fo);
     memcpy(fh.magic, "H264B2RP", 8); fh.version = 1; fh.width_mbs = (uint32_t)wmb; fh.height_mbs = (uint32_t)hmb; fh.n_pics = (uint32_t)n_pics; fh.n_out = (uint32_t)outs.size();
     fh.hdr_bytes = sizeof fh; fh.pichdr_bytes = sizeof(H264B2FrontPicHdr);
     fseek(fo, 0, SEEK_SET); fwrite(&fh, sizeof fh, 1, fo); fclose(fo);

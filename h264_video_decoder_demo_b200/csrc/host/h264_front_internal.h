@@ -152,7 +152,7 @@ struct Cabac {
         const uint32_t lps = V >= scaled;                 // 1: least probable symbol
         V -= lps ? scaled : 0;
         uint32_t r = lps ? rlps : rmps;
-        state[ctx] = g_next_state[0][(lps << 7) | s];      // [1][s] follows [0][127]
+        state[ctx] = (&g_next_state[0][0])[(lps << 7) | s];      // the table as one array of 256: [1][s] follows [0][127]
         const int n = __builtin_clz(r) - 23;               // r in [6, 510] -> 0..6 (0 or 1 after an MPS)
         range = r << n;
         if (k < n) refill();

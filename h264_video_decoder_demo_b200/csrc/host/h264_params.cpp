@@ -276,7 +276,7 @@ int parse_slice_header(BitReader &br, int nal_ref_idc, int nal_unit_type, const 
     sh.PicSizeInMbs = sps.PicWidthInMbs * sh.PicHeightInMbs;
     sh.MaxPicNum = sh.field_pic_flag ? 2 * sps.MaxFrameNum : sps.MaxFrameNum;
     sh.CurrPicNum = sh.field_pic_flag ? 2 * sh.frame_num + 1 : sh.frame_num;
-    sh.FilterOffsetA = sh.slice_alpha_c0_offset_div2 << 1; sh.FilterOffsetB = sh.slice_beta_offset_div2 << 1;
+    sh.FilterOffsetA = sh.slice_alpha_c0_offset_div2 * 2; sh.FilterOffsetB = sh.slice_beta_offset_div2 * 2;
     set_scaling_lists(sh);
     return 0;
 }
