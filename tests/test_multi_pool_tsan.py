@@ -53,3 +53,23 @@ def test_closed_gop_units_under_tsan(tsan_exe):
         pytest.skip("fixture missing")
     got = _run(tsan_exe, 3, 4, 1 | 2, [f])             # READBACK | SPLIT_GOPS: 1080p blocks through the pool, GOP pre-scan
     assert got["pictures"] == got["frames_out"] > 0 and got["pictures"] % 4 == 0 and len(set(got["hashes"])) == 1
+
+
+def test_decoder_facade_producer_thread_under_tsan(tmp_path):
+    """CH264VideoDecoder::open (the same-name shim over csrc/host/H264VideoDecoderB200.cpp): the front end runs on a producer thread, the
+    callback on the calling thread, picture blocks go back to the pool from the consumer side — all of it under ThreadSanitizer against
+    the engine test double; the callback protocol (frames in output order, final NULL + FILE_END) is checked by the client itself."""
+    exe = str(tmp_path / "shim_tsan")
+    srcs = [os.path.join(HERE, "shim_main_check.cpp"), os.path.join(HERE, "mock_engine.cpp")] + [os.path.join(HOST, f) for f in ("H264VideoDecoderB200.cpp", "h264_multi.cpp", "h264_front.cpp", "h264_slice.cpp", "h264_params.cpp")]
+    r = subprocess.run(["g++", "-O1", "-g", "-fsanitize=thread", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", HOST, "-o", exe] + srcs + ["-pthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("ThreadSanitizer build not available: " + r.stderr[-300:])
+    out = tmp_path / "bmp"
+    out.mkdir()
+    for name in ("synth_b_direct.first7.h264", "synth_mmco_lt_36.first9.h264", "HeavyHand_1080p.B_frames_cabac_tff.first7.h264"):
+        f = os.path.join(HERE, "golden", name)
+        if not os.path.exists(f):
+            continue
+        r = subprocess.run([exe, f, str(out)], capture_output=True, text=True, timeout=600)
+        assert "ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
+        assert r.returncode == 0 and "end_seen=1" in r.stdout, r.stdout[-500:] + r.stderr[-500:]
