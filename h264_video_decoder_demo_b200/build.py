@@ -47,13 +47,35 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the B200 engine cannot be built (there is no CPU fallback)")
 
 
+def _code_only(text):
+    """C/C++ source without comments and with white space collapsed (string and character literals are kept as they are)."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        c = text[i]
+        if c == '"' or c == "'":
+            j = i + 1
+            while j < n and text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            out.append(text[i:j + 1]); i = j + 1
+        elif text.startswith("//", i):
+            j = text.find("\n", i)
+            i = n if j < 0 else j
+        elif text.startswith("/*", i):
+            j = text.find("*/", i + 2)
+            out.append(" "); i = n if j < 0 else j + 2
+        else:
+            out.append(c); i += 1
+    return " ".join("".join(out).split())
+
+
 def source_hash():
-    """SHA-1 over the CUDA engine's sources (the compiled library is not bit-reproducible): what profiles/traffic_r02.json is keyed by."""
+    """SHA-1 over the CODE of the CUDA engine's sources — comments stripped, white space collapsed — because the compiled library is not
+    bit-reproducible and a comment must not orphan a profile: what profiles/traffic_r02.json is keyed by."""
     import hashlib
     h = hashlib.sha1()
     for f in sorted([os.path.join(CSRC, x) for x in SOURCES + HEADERS] + [os.path.join(_ROOT, "include", "h264_recon_b200.h")]):
         h.update(os.path.basename(f).encode())
-        h.update(open(f, "rb").read())
+        h.update(_code_only(open(f, encoding="utf-8", errors="replace").read()).encode())
     return h.hexdigest()
 
 

@@ -3,11 +3,17 @@
 // One context = one GPU.  A submit reconstructs one picture for each listed stream (pictures of one
 // stream are serial in decoding order; different streams are independent and share every launch):
 //
+//   launch stream
 //   [memset of surfaces that must start from zero (PB:53-69)]
-//   k_inter    inter prediction + inter residual        (fully parallel, one CTA per macroblock)
-//   k_intra    intra prediction + intra residual        (MB wavefront, one warp per MB row)
-//   k_bs       boundary strengths                        (fully parallel)
-//   k_deblock  in-loop filter, in place                  (MB wavefront, one warp per MB row)
+//   k_inter_tma   inter prediction + inter residual, reference windows staged by TMA   (warp per 5 consecutive macroblocks)
+//   k_inter_list  the inter macroblocks k_inter_tma left on the work list              (warp per macroblock, clamped loads)
+//   k_inter       MBAFF pictures / H264B2_INTER_V1                                     (warp per macroblock)
+//   k_intra       intra prediction + intra residual: luma and chroma wavefronts        (MB wavefront, one warp per MB row, band CTAs)
+//   k_deblock3    in-loop filter, in place, four pictures per warp                     (MB wavefront; k_deblock<true> for MBAFF)
+//   look-ahead stream, one batch ahead
+//   k_prologue [k_expand, k_unmotion]  descriptors, packed levels / motion records -> plain arrays
+//   k_residual    dequantisation + inverse transforms into the residual tiles          (warp per macroblock)
+//   k_bs_prog2    boundary strengths as step codes                                      (thread per macroblock; k_bs for MBAFF)
 //
 // The decoded picture buffer (n_streams x surfaces_per_stream I420 surfaces, Y|Cb|Cr contiguous like
 // PB:167-179) lives in HBM for the life of the context.  There is no CPU fallback anywhere.
