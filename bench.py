@@ -220,6 +220,16 @@ def measure_config(name, stems_, S, local_rank, world, max_pictures=None):
             "kernel_ms": {k: round(v["ms"], 1) for k, v in kt.items()}}
 
 
+_T0 = time.time()
+
+
+def phase(msg):
+    """Progress line on stderr (rank 0 only; stdout carries nothing but the one JSON line)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("bench [%6.1f s] %s\n" % (time.time() - _T0, msg))
+        sys.stderr.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -407,6 +417,7 @@ def main():
         for b in batches:
             eng.submit_prepared(b)
 
+    phase("%d replicas resident, batches prepared" % S)
     # ---- warm-up (the last warm-up step is checked against the reference's checksums, every stream, every picture)
     for w in range(max(args.warmup, 1)):
         if w == max(args.warmup, 1) - 1:
@@ -419,6 +430,7 @@ def main():
             step()
     eng.sync()
 
+    phase("warm-up done, parity checked against the reference's checksums")
     # ---- timed region: device time by CUDA events on the launch stream, max over ranks
     sampler = ClockSampler(local_rank)
     time.sleep(0.3)
@@ -451,6 +463,7 @@ def main():
     if eng.checksums(sids, dst[-1]) != want[-1]:
         raise SystemExit("PARITY FAILURE after the timed region")
 
+    phase("timed steps done")
     # ---- roofline of the dominant kernel
     abv = [algorithmic_bytes(v["rp"]) for v in variants]
     per_step = {k: sum(abv[var_of[s]][pic_of(s, i)][k] for s in sids for i in range(npic)) for k in ("inter", "intra", "deblock")}
@@ -502,6 +515,7 @@ def main():
     kernels["deblock"]["of_which_bs_ms"] = round(kt["bs"]["ms"] / kt_steps, 3)
     launches = sum(kt[k]["launches"] for k in ("residual", "inter", "intra", "bs", "deblock")) * args.steps
 
+    phase("per-kernel timing done")
     # ---- e2e: host buffers in, host pictures out, through the C ABI
     e2e = None
     if not args.no_e2e:
@@ -586,6 +600,7 @@ def main():
                "kernel_ms_per_step": {k: round(v["ms"] / args.e2e_steps, 1) for k, v in e2e_kt.items()}, "timing": "host wall clock around submit+read-back of every picture, synchronised on both sides, max over ranks"}
 
     l2_gb = (sum(sum(r.blob_bytes) for r in rs) + 17 * eng.frame_bytes * S) / 1e9
+    phase("e2e leg done")
     # ---- the whole decoder: Annex-B in, pictures out (host entropy/derivation stage on a thread pool + the CUDA engine)
     e2e_bits = None
     stream_files = [os.path.join(REF_DIR, "streams", st + ".h264") for st in stems]
@@ -612,6 +627,7 @@ def main():
                     "checked": "every stream's output-order checksum chain equals the reference decoder's" if hashes_want is not None else "not checked (prefix fixtures)",
                     "what": "h264b2_multi_decode: Annex-B byte streams in, every output picture in page-locked host memory; host entropy decoding + derivations included"}
 
+    phase("whole-decoder leg done")
     # ---- the other BASELINE.json configurations, shortly (device-resident replay, parity-checked): config 3 (field/MBAFF stream), config 4
     #      (the long-GOP stream; it has ONE closed GOP, so GOP-parallelism is shown on the two-GOP HeavyHand stream by the tests and the
     #      multi-stream pipeline), config 5 (64 streams of all five variants, STRONG scaling: 64 / N streams per GPU)
@@ -632,6 +648,7 @@ def main():
         configs["mixed_64_streams"] = dict(measure_config("mixed", [WORKLOADS[w] for w in MIXED], per_gpu, local_rank, world), baseline_config=5, scaling="strong",
                                            note="64 streams in total, all five bundled variants round-robin, 64 / n_gpus per GPU")
 
+    phase("configs block done")
     # ---- CPU baseline: the unmodified reference on one host core (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
